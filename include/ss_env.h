@@ -1,0 +1,124 @@
+/*
+ * ss_env.h -- C-ABI of the B200 batched stepping-stone environment (libss_b200.so).
+ *
+ * The reference has no native FFI: its operator boundary for this path is the Python vectorised-env
+ * protocol of common/envs_utils.py (ShmemVecEnv, :486-620) over N copies of
+ * mocca_envs:Walker3DStepperEnv-v0 / MikeStepperEnv-v0.  Each entry point below names the reference
+ * interface it replaces; steppingstone_b200/vec_env.py binds them with ctypes and INTEGRATION.md shows
+ * the reference-side stub.
+ *
+ * Conventions: every function returns 0 on success and a negative code on error (ss_last_error()
+ * gives the text, thread-local).  Pointers named *_dev are device pointers owned by the caller
+ * (torch CUDA tensors); *_host are host pointers.  `stream` is a cudaStream_t passed as void*
+ * (torch.cuda.current_stream().cuda_stream); all device work is enqueued on it and nothing
+ * synchronises unless stated.  A handle belongs to one device and is not thread-safe (like the
+ * reference: strictly call-and-wait, envs_utils.py:550-558).
+ */
+#ifndef SS_ENV_H
+#define SS_ENV_H
+#include <stdint.h>
+#include "ss_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_OK 0
+#define SS_ERR_ARG (-1)
+#define SS_ERR_CUDA (-2)
+#define SS_ERR_STATE (-3)
+
+#define SS_NWARM 32      /* warm-start cache slots: capsule*8 + (stone&3)*2 + endpoint            */
+#define SS_NSCAL 16      /* doubles per env in ss_state_view.scalars                              */
+#define SS_NINT 8        /* int32 per env in ss_state_view.ints                                   */
+#define SS_MT_WORDS 625  /* MT19937: 624 state words + position                                   */
+
+/* scalars[]: */
+enum { SS_S_POTENTIAL = 0, SS_S_WALK_X, SS_S_WALK_Y, SS_S_WALK_Z, SS_S_INITIAL_Z,
+       SS_S_FEET_CONTACT0, SS_S_FEET_CONTACT1, SS_S_FEET_X0 /* ..+5: feet_xyz[2][3] */,
+       SS_S_EP_RET = 13, SS_S_CACHE_CONTACT0 = 14, SS_S_CACHE_CONTACT1 = 15 };
+/* ints[]: */
+enum { SS_I_NEXT_STEP = 0, SS_I_REACHED_COUNT, SS_I_MIRRORED, SS_I_ELAPSED, SS_I_EP_LEN,
+       SS_I_UPDATE_TERRAIN, SS_I_PHANTOM_IDX, SS_I_STARTED };
+
+/* Full simulator state of N envs in host memory (teacher forcing, checkpoints, parity tests).
+ * NULL members are skipped.  Reference analogue: none (env state is never saved). */
+typedef struct ss_state_view {
+    double* q;         /* [N,28] base xyz, base quat (x,y,z,w), 21 hinge angles                   */
+    double* qd;        /* [N,27] base angular vel (world), base linear vel (world), 21 hinge rates */
+    double* warm;      /* [N,32] cached normal impulses (Bullet manifold warm starting)           */
+    double* terrain;   /* [N,n_steps,6] terrain_info: x,y,z,phi,x_tilt,y_tilt                     */
+    double* plank;     /* [N,rendered,6] pose each plank body was last given                      */
+    double* scalars;   /* [N,SS_NSCAL]                                                            */
+    int32_t* ints;     /* [N,SS_NINT]                                                             */
+    uint32_t* mt;      /* [N,2,SS_MT_WORDS] env np_random stream, then the env's copy of the global numpy stream */
+} ss_state_view;
+
+typedef struct ss_env ss_env;
+
+/* make_vec_envs(env_id, seed, num_processes, log_dir) -- common/envs_utils.py:48-56, one gym env per
+ * worker seeded seed+rank (:25-40).  mt_env_host [n_envs,625] / mt_global_host [625] are the MT19937
+ * states of gym's per-env RandomState(seed+rank) and of the forked global numpy stream (q7); the
+ * Python host derives them (steppingstone_b200/seeding.py).  first_env is the global index of this
+ * shard's env 0 (multi-GPU sharding keeps global numbering). */
+int ss_create(const ss_model* model, const ss_params* params, int32_t n_envs, int32_t device,
+              const uint32_t* mt_env_host, const uint32_t* mt_global_host, ss_env** out);
+/* VecEnv.close -- envs_utils.py:273-281 */
+void ss_destroy(ss_env* env);
+
+/* ShmemVecEnv.reset -- envs_utils.py:542-548 -> Walker3DStepperEnv.reset walker3d_envs.py:812-867 /
+ * MikeStepperEnv.reset mike.py:333-388.  obs_dev [N,60] f32. */
+int ss_reset_all(ss_env* env, float* obs_dev, void* stream);
+
+/* ShmemVecEnv.step_async+step_wait -- envs_utils.py:550-558; worker loop with auto-reset :645-649;
+ * Walker3DStepperEnv.step walker3d_envs.py:875-903; Monitor.update envs_utils.py:130-153;
+ * TimeLimitMask.step :60-65.  act_dev [N,21] f32; obs_dev [N,60] f32 (post-reset obs for finished
+ * envs); rew_dev [N] f32; done_dev [N] u8; timeout_dev [N] u8 (info["bad_transition"]);
+ * ep_ret_dev [N] f32 / ep_len_dev [N] i32 = info["episode"]["r"/"l"], valid where done. */
+int ss_step(ss_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
+            uint8_t* timeout_dev, float* ep_ret_dev, int32_t* ep_len_dev, void* stream);
+
+/* Same call with HOST buffers (the reference's numpy-in / numpy-out contract): copies actions in,
+ * steps, copies the five result arrays out through pinned staging, and synchronises. */
+int ss_step_host(ss_env* env, const float* act_host, float* obs_host, float* rew_host,
+                 uint8_t* done_host, uint8_t* timeout_host, float* ep_ret_host, int32_t* ep_len_host);
+int ss_reset_host(ss_env* env, float* obs_host);
+
+/* update_curriculum / update_specialist / update_sample_prob -- walker3d_envs.py:1346-1356, :604-622,
+ * :1317-1320 (mike.py:856-866, :827-830) through envs_utils.py:568-586.  The caller passes the
+ * normalised cumulative table exactly as RandomState.choice builds it (cdf = cumsum(p/p.sum());
+ * cdf /= cdf[-1]); n_cells must be 11^5.  One table shared by all envs (train.py:269-271 broadcasts
+ * one table).  apply_now != 0 reproduces update_sample_prob's immediate re-sample of the next-next
+ * stone for envs whose update_terrain flag is set. */
+int ss_set_sample_cdf(ss_env* env, const double* cdf_host, int32_t n_cells, int32_t apply_now, void* stream);
+
+/* State access (synchronous). */
+int ss_get_state(ss_env* env, ss_state_view* view);
+int ss_set_state(ss_env* env, const ss_state_view* view);
+
+/* Per-substep parity probe (SURVEY 8b ss_substep_trace): after each ss_step the library keeps the
+ * generalised coordinates reached after each of the 4 physics substeps.  q_host [4,N,28],
+ * qd_host [4,N,27] doubles.  Must be enabled first (costs 1.76 KB/env of extra stores per step). */
+int ss_enable_substep_trace(ss_env* env, int32_t on);
+int ss_substep_trace(ss_env* env, double* q_host, double* qd_host);
+
+/* Stand-alone articulated-body forward-dynamics substep (no contacts, no limits): the
+ * `aba_substep` kernel boundary of SURVEY 8(d) -- reads q [N,28], qd [N,27], tau [N,21] (f32, device),
+ * writes q, qd in place; 524 algorithmic bytes per env-substep. */
+int ss_aba_substep(ss_env* env, float* q_dev, float* qd_dev, const float* tau_dev, int32_t n, void* stream);
+
+/* Device-side GAE scan: RolloutStorage.compute_returns(use_gae=True) -- algorithms/storage.py:59-71.
+ * rewards [T,N], value_preds [T+1,N], masks [T+1,N], bad_masks [T+1,N], returns [T+1,N] (f32, device). */
+int ss_gae(const float* rewards_dev, const float* value_preds_dev, const float* masks_dev,
+           const float* bad_masks_dev, float* returns_dev, int32_t T, int32_t N, float gamma,
+           float gae_lambda, void* stream);
+
+int32_t ss_num_envs(const ss_env* env);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t ss_launch_count(const ss_env* env);
+const char* ss_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

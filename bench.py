@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the stepping-stone hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 256 --warmup 32
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU arm: the oracle port on all host threads
+
+A "step" = one control step (4 physics substeps at 240 Hz, 20 solver iterations each, observation, reward,
+termination, auto-reset) of every env of the batch.  Workload at N=1 is BASELINE.json configs[1]:
+Walker3DStepperEnv-v0, 8192 envs per GPU, flat-terrain stage, actions clip(N(0, e^-1.5), -1, 1).
+Prints ONE JSON line on rank 0 (contract in the task statement; keys documented in DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_ENV_STEP = 884      # fused env-step boundary, fp32
+ALG_BYTES_PER_ENV_SUBSTEP = 524   # aba_substep kernel boundary, fp32
+H2D_PER_ENV = 21 * 4
+D2H_PER_ENV = 60 * 4 + 4 + 1 + 1 + 4 + 4
+WORKLOADS = {
+    "w3d-flat": dict(env_id="mocca_envs:Walker3DStepperEnv-v0", kind=0, terrain_mode=2, curriculum=None,
+                     name="Walker3DStepperEnv-v0 flat-terrain stage, 240 Hz / 4 substeps, 20 PGS iters"),
+    "w3d": dict(env_id="mocca_envs:Walker3DStepperEnv-v0", kind=0, terrain_mode=None, curriculum=None,
+                name="Walker3DStepperEnv-v0 as shipped (+-30 deg up/down terrain)"),
+    "mike": dict(env_id="mocca_envs:MikeStepperEnv-v0", kind=1, terrain_mode=None, curriculum=5,
+                 name="MikeStepperEnv-v0 use_curriculum (level 5: yaw +-20, pitch +-50)"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, seed=8):
+    """env-steps/s of the CPU oracle (C port of the reference algorithm) on the host cores."""
+    from oracle.binding import Oracle
+    from steppingstone_b200 import model, seeding
+    M = model.make_model(wl["kind"])
+    P = model.make_params(wl["kind"], None, wl["terrain_mode"])
+    o = Oracle(M, P, n_envs, seeding.env_streams(seed, 0, n_envs), seeding.global_stream(seed), threads=threads)
+    if wl["curriculum"] is not None:
+        o.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(wl["curriculum"])))
+    o.reset()
+    rng = np.random.RandomState(0)
+    acts = [np.clip(rng.randn(n_envs, 21) * 0.22, -1, 1).astype(np.float32) for _ in range(8)]
+    for i in range(warmup):
+        o.step(acts[i % 8])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        o.step(acts[i % 8])
+    dt = time.perf_counter() - t0
+    o.close()
+    return n_envs * steps / dt, dt
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path.  PyBullet (where the reference's
+    physics lives) is absent from the reference tree and from this image, so this arm times the oracle port
+    (kind "port") on all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = args.ref_envs
+    rate, dt = cpu_port_rate(wl, n_envs, args.steps, args.warmup)
+    sample = "%d envs x %d steps (of the %d-env workload), %d OpenMP threads" % (n_envs, args.steps, args.envs, cores)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_step": n_envs, "actions": "clip(N(0,0.22),-1,1)"},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+    from steppingstone_b200 import BatchedStepperEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, K, W = args.envs, args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    env = BatchedStepperEnv(wl["env_id"], 8, N, device=local, output="torch", first_env=rank * N,
+                            terrain_mode=wl["terrain_mode"])
+    if wl["curriculum"] is not None:
+        env.update_curriculum(wl["curriculum"])
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(rank)
+    ring = 64
+    acts = torch.clamp(torch.randn(ring, N, 21, device=dev, generator=gen) * 0.22, -1, 1).contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    for i in range(W):
+        env.step(acts[i % ring])
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    l0 = env.launch_count
+    done_count = torch.zeros((), dtype=torch.int64, device=dev)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xff)                      # L2 flush between timed steps (outside the event pair)
+        ev[i][0].record()
+        _, _, done, _ = env.step(acts[(W + i) % ring])
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = env.launch_count - l0
+    clocks = sampler.stop()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    t_dev = float(step_ms.sum()) * 1e-3
+    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    value = world * N * K / t_max
+
+    # ---- end to end through the reference-facing call with HOST buffers (ss_step_host) ----
+    env_h = BatchedStepperEnv(wl["env_id"], 8, N, device=local, output="numpy", first_env=rank * N,
+                              terrain_mode=wl["terrain_mode"])
+    if wl["curriculum"] is not None:
+        env_h.update_curriculum(wl["curriculum"])
+    env_h.reset()
+    acts_h = acts.cpu().numpy()
+    Ke = max(8, min(K, 64))
+    for i in range(3):
+        env_h.step(acts_h[i % ring])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        obs_h, rew_h, done_h, infos_h = env_h.step(acts_h[(3 + i) % ring])
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * Ke / float(te.item())
+    env_h.close()
+
+    # ---- stand-alone ABA (forward dynamics) kernel: the 524 B / env-substep boundary ----
+    q = torch.zeros(N, 28, device=dev); q[:, 6] = 1.0
+    q[:, 7:] = (torch.rand(N, 21, device=dev, generator=gen) - 0.5)
+    qd = torch.randn(N, 27, device=dev, generator=gen)
+    tau = torch.randn(N, 21, device=dev, generator=gen) * 20
+    for _ in range(5):
+        env.aba_substep(q, qd, tau)
+    torch.cuda.synchronize(dev)
+    aba_ms = []
+    for i in range(20):
+        flush.fill_(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); env.aba_substep(q, qd, tau); b.record()
+        torch.cuda.synchronize(dev)
+        aba_ms.append(a.elapsed_time(b))
+    aba_s = float(np.mean(aba_ms)) * 1e-3
+
+    peak, peak_src = measured_peaks()
+    kern_s = t_dev / K
+    achieved = ALG_BYTES_PER_ENV_STEP * N / kern_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("env_step_kernel_dram_bytes_per_launch")
+    aba_achieved = ALG_BYTES_PER_ENV_SUBSTEP * N / aba_s / 1e9
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_cpu, k_cpu = args.ref_envs, 16
+            rate, dt = cpu_port_rate(wl, n_cpu, k_cpu, 2)
+            cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                   "sample": "%d envs x %d steps of the same workload, %d OpenMP threads, %.1f s" % (n_cpu, k_cpu, cores, dt)}
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": t_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "envs_per_gpu": N, "global_envs": world * N,
+                       "actions": "clip(N(0,0.22),-1,1), 64-batch ring resident in HBM", "parallelism": "env-sharded x%d" % world,
+                       "l2": "flushed between timed steps (256 MiB write outside the event pair)",
+                       "timing": "sum of per-step CUDA-event durations, max over ranks",
+                       "wall_ms_per_step_incl_flush": t_wall / K * 1e3},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * H2D_PER_ENV,
+                    "d2h_bytes_per_step": N * D2H_PER_ENV, "steps": Ke, "api": "BatchedStepperEnv.step (numpy mode) -> ss_step_host"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "env_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "avg_launch_ms": kern_s * 1e3,
+                         "note": "FP32-latency bound path (SURVEY 8d): the HBM fraction is reported as asked, not a target"},
+            "roofline_aba": {"kernel": "aba_substep_kernel", "bound": "hbm", "achieved": aba_achieved, "peak": peak, "unit": "GB/s",
+                             "frac": aba_achieved / peak, "traffic": None, "avg_launch_ms": aba_s * 1e3,
+                             "algorithmic_bytes_per_env_substep": ALG_BYTES_PER_ENV_SUBSTEP,
+                             "env_substeps_per_s": N / aba_s},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=8192, help="envs per GPU")
+    ap.add_argument("--workload", default="w3d-flat", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-envs", type=int, default=256, help="envs per step of the CPU arm's bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

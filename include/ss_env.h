@@ -113,6 +113,16 @@ int ss_gae(const float* rewards_dev, const float* value_preds_dev, const float* 
            const float* bad_masks_dev, float* returns_dev, int32_t T, int32_t N, float gamma,
            float gae_lambda, void* stream);
 
+/* Parity probes (tests only; no reference analogue).
+ * ss_env_post: calc_state + calc_env_state on the CURRENT state without stepping the physics
+ *   (robots.py:304-365 + walker3d_envs.py:1026-1044), no TimeLimit/Monitor/auto-reset.
+ * ss_enable_debug / ss_debug_read: per-env dump of the last substep's joint-space inertia H [27,27], bias C [27],
+ *   contact candidates [32,8], row constants and Delassus matrix; out_host [N, ss_debug_floats()] f32. */
+int ss_env_post(ss_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream);
+int32_t ss_debug_floats(void);
+int ss_enable_debug(ss_env* env, int32_t on);
+int ss_debug_read(ss_env* env, float* out_host);
+
 int32_t ss_num_envs(const ss_env* env);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ss_launch_count(const ss_env* env);

@@ -812,8 +812,12 @@ static void env_reset(const struct sso_env* S, env_t* e, float* obs) {
     memset(e->qdj, 0, sizeof e->qdj);
     memcpy(e->pos, M->init_pos, 24);
     e->quat[0] = e->quat[1] = e->quat[2] = 0; e->quat[3] = 1;
-    e->v[0] = e->v[1] = e->v[2] = 0;                                     /* angular velocity is NOT reset: q3 */
-    if (!isfinite(e->w[0] + e->w[1] + e->w[2])) e->w[0] = e->w[1] = e->w[2] = 0;   /* deviation: do not let a NaN survive a reset */
+    /* robots.py:612-616: resetBasePositionAndOrientation then resetBaseVelocity(linearVelocity=vel).  The
+     * second call leaves the angular velocity untouched, but Bullet's init-pose command behind
+     * the first one zeroes BOTH base velocities whenever it sets position+orientation, so the net effect is
+     * w = v = 0 after every reset. */
+    e->v[0] = e->v[1] = e->v[2] = 0;
+    e->w[0] = e->w[1] = e->w[2] = 0;
     /* WalkerBase.reset robots.py:433-439 */
     e->feet_contact[0] = e->feet_contact[1] = 0;
     memset(e->feet_xyz, 0, sizeof e->feet_xyz);

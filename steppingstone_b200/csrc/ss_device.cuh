@@ -1,0 +1,774 @@
+// ss_device.cuh -- warp-per-env device code of the B200 stepping-stone environment (sm_100a).
+//
+// One warp owns one env for a whole control step.  Three lane mappings are used:
+//   lane = body  (22 bodies)   kinematics, composite inertia, bias forces      -> tree scans with __shfl
+//   lane = dof   (27 dofs)     LDL^T factorisation, velocity / position update
+//   lane = row   (<=32 rows)   constraint rows, Delassus matrix, projected Gauss-Seidel
+// Spatial quantities live in ONE frame per substep: world-aligned axes, origin at the base link's
+// origin ("common frame"), so tree accumulations are plain sums (no per-link spatial transforms).
+//
+// Reference call sites replaced: pybullet.stepSimulation via World.step (mocca_envs/bullet_utils.py:331-332)
+// and the env logic of mocca_envs/walker3d_envs.py:875-1093 / mocca_envs/mike.py:396-603.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "ss_env.h"
+
+#define FULL 0xffffffffu
+#define SS_PI_D 3.14159265358979323846
+#define SS_DEG_D (SS_PI_D / 180.0)
+
+namespace ssb {
+
+constexpr int NB = SS_NB, NJ = SS_NJ, ND = SS_NDOF;
+constexpr int HS = 29;   // row stride of H / L in shared memory (odd -> conflict-free row-per-lane access)
+constexpr int ZS = 29;   // row stride of Z
+constexpr int AS = 33;   // row stride of A
+constexpr int MAXC = SS_MAX_CONTACTS, MAXL = SS_MAX_LIMIT_ROWS;
+
+// ---------------------------------------------------------------------------------------------
+// constant tables (fp32 copy of ss_model + ss_params), staged into shared memory with one TMA bulk copy
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) DevModel {
+    float anchor[NB][3]; float R0[NB][9]; float axis[NB][3]; float mass[NB]; float com[NB][3]; float inertia[NB][6];
+    float q_lo[NJ], q_hi[NJ], tau_max[NJ], damping[NJ], pd_p[NJ], pd_d[NJ], init_q[NJ];
+    float col_p0[SS_NCOL][3], col_p1[SS_NCOL][3], col_radius[SS_NCOL];
+    int col_body[SS_NCOL], col_foot[SS_NCOL];
+    int foot_body[2]; float foot_ref[2][3];
+    int anc_mask[NB];
+    float contact_breaking, gravity, dt, erp_limit, cfm_contact, erp_contact, friction, linear_slop, warmstart,
+        max_coord_vel, limit_max_impulse, stone_half[3], stone_box_off, stone_com_z;
+    int n_substeps, n_iters, robot_kind, terrain_mode, n_steps, rendered, stop_frames, max_episode_steps,
+        n_phantoms, use_sampler, actuator_mode, pad0;
+    float done_height, electricity_cost, stall_torque_cost, joints_at_limit_cost;
+    double init_pos[3], step_radius, r_max, tilt_limit_deg, mirror_prob, control_dt;
+    double samples[5][SS_GRID];     // yaw, pitch, r, x_tilt, y_tilt
+    double pad1;
+};
+static_assert(sizeof(DevModel) % 16 == 0, "DevModel must be a multiple of 16 bytes for cp.async.bulk");
+
+struct DevState {
+    double* pos;        // [N][3]   base position (world, double: courses run to x ~ 70 m)
+    float* sv;          // [N][64]  0..3 quat xyzw, 4..24 hinge angles, 32..58 generalised velocity (ang3, lin3, hinge21)
+    float* warm;        // [N][32]
+    double* terrain;    // [N][n_steps][6]
+    double* plank;      // [N][rendered][6]
+    double* scal;       // [N][SS_NSCAL]
+    int* ints;          // [N][SS_NINT]
+    uint32_t* mt;       // [N][2][SS_MT_WORDS]
+    const double* cdf;  // [n_cells]
+    int n_cells;
+    double* trace_q;    // [4][N][28] or null
+    double* trace_qd;   // [4][N][27] or null
+    float* dbg;         // [N][DBG_FLOATS] or null
+    int n;
+};
+constexpr int DBG_H = 0, DBG_C = 729, DBG_CAND = 756, DBG_ROWS = 756 + 256, DBG_FLOATS = 756 + 256 + 4 + 32 * 6 + 32 * 32;
+
+// per-warp scratch
+struct alignas(16) WarpSmem {
+    float S[NB][6];
+    float foot[2][12];
+    float stone[4][16];       // per candidate slot: box centre rel. step-start base pos (3), R (9), valid, pad
+    float vec[64];            // v* (27) / obs staging (60)
+    float con[MAXC][12];      // n3, x3, depth, body, slot
+    float lim[MAXL][4];       // hinge, dir, penetration
+    float dinv[32];
+    union {
+        struct { float H[ND * HS]; float Z[32 * ZS]; float A[32 * AS]; } s;
+        double d[(ND * HS + 32 * ZS + 32 * AS) / 2];
+    } u;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ float shfl(float v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* c) {
+    float t0 = a[1] * b[2] - a[2] * b[1], t1 = a[2] * b[0] - a[0] * b[2], t2 = a[0] * b[1] - a[1] * b[0];
+    c[0] = t0; c[1] = t1; c[2] = t2;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void matvec3(const float* R, const float* x, float* y) {
+    float t0 = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
+    float t1 = R[3] * x[0] + R[4] * x[1] + R[5] * x[2];
+    float t2 = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
+    y[0] = t0; y[1] = t1; y[2] = t2;
+}
+__device__ __forceinline__ void matTvec3(const float* R, const float* x, float* y) {
+    float t0 = R[0] * x[0] + R[3] * x[1] + R[6] * x[2];
+    float t1 = R[1] * x[0] + R[4] * x[1] + R[7] * x[2];
+    float t2 = R[2] * x[0] + R[5] * x[1] + R[8] * x[2];
+    y[0] = t0; y[1] = t1; y[2] = t2;
+}
+__device__ __forceinline__ void matmul3(const float* A, const float* B, float* C) {
+    float T[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) T[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) C[i] = T[i];
+}
+__device__ __forceinline__ void quat_to_mat(const float* q, float* R) {
+    float x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// topology of the humanoid tree (SS_PARENT_TABLE): chains 1..8, 9..13 (off body 3), 14..17 and 18..21 (off the base)
+__device__ __forceinline__ int seg_start(int l) { return l == 0 ? 0 : (l <= 8 ? 1 : (l <= 13 ? 9 : (l <= 17 ? 14 : (l <= 21 ? 18 : l)))); }
+__device__ __forceinline__ int seg_end(int l) { return l == 0 ? 0 : (l <= 8 ? 8 : (l <= 13 ? 13 : (l <= 17 ? 17 : (l <= 21 ? 21 : l)))); }
+
+// sum over the subtree rooted at each body (lanes >= 22 must pass 0)
+__device__ __forceinline__ float subtree_sum(float x, int lane, int send) {
+#pragma unroll
+    for (int off = 1; off <= 4; off <<= 1) { float y = __shfl_down_sync(FULL, x, off); if (lane + off <= send) x += y; }
+    float t9 = shfl(x, 9); if (lane >= 1 && lane <= 3) x += t9;
+    float t1 = shfl(x, 1), t14 = shfl(x, 14), t18 = shfl(x, 18);
+    if (lane == 0) x += t1 + t14 + t18;
+    return x;
+}
+// sum over the ancestors of each body including itself and the base (lane 0)
+__device__ __forceinline__ float tree_prefix(float x, int lane, int sstart) {
+#pragma unroll
+    for (int off = 1; off <= 4; off <<= 1) { float y = __shfl_up_sync(FULL, x, off); if (lane >= 1 && lane - off >= sstart) x += y; }
+    float t3 = shfl(x, 3); if (lane >= 9 && lane <= 13) x += t3;
+    float t0 = shfl(x, 0); if (lane >= 1 && lane < NB) x += t0;
+    return x;
+}
+
+struct Xf { float R[9]; float p[3]; };
+__device__ __forceinline__ Xf xf_shfl_up(const Xf& a, int off) {
+    Xf r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.R[i] = __shfl_up_sync(FULL, a.R[i], off);
+#pragma unroll
+    for (int i = 0; i < 3; i++) r.p[i] = __shfl_up_sync(FULL, a.p[i], off);
+    return r;
+}
+__device__ __forceinline__ Xf xf_shfl(const Xf& a, int src) {
+    Xf r;
+#pragma unroll
+    for (int i = 0; i < 9; i++) r.R[i] = shfl(a.R[i], src);
+#pragma unroll
+    for (int i = 0; i < 3; i++) r.p[i] = shfl(a.p[i], src);
+    return r;
+}
+// a o b : x -> a.R (b.R x + b.p) + a.p
+__device__ __forceinline__ Xf xf_compose(const Xf& a, const Xf& b) {
+    Xf r; float t[3];
+    matmul3(a.R, b.R, r.R);
+    matvec3(a.R, b.p, t);
+    r.p[0] = a.p[0] + t[0]; r.p[1] = a.p[1] + t[1]; r.p[2] = a.p[2] + t[2];
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward kinematics: lane b gets the pose of body b in the common frame (rotation to world axes,
+// origin relative to the base origin)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ Xf fk_warp(const DevModel& M, const float* quat, float q_dof, int lane) {
+    float qb = shfl(q_dof, (lane + 5) & 31);
+    Xf X;
+#pragma unroll
+    for (int i = 0; i < 9; i++) X.R[i] = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+    X.p[0] = X.p[1] = X.p[2] = 0.f;
+    if (lane == 0) quat_to_mat(quat, X.R);
+    else if (lane < NB) {
+        float s, c; sincosf(qb, &s, &c);
+        float t = 1.f - c, x = M.axis[lane][0], y = M.axis[lane][1], z = M.axis[lane][2];
+        float Rj[9] = { t * x * x + c, t * x * y - s * z, t * x * z + s * y,
+                        t * x * y + s * z, t * y * y + c, t * y * z - s * x,
+                        t * x * z - s * y, t * y * z + s * x, t * z * z + c };
+        matmul3(M.R0[lane], Rj, X.R);
+        X.p[0] = M.anchor[lane][0]; X.p[1] = M.anchor[lane][1]; X.p[2] = M.anchor[lane][2];
+    }
+    int ss = seg_start(lane);
+#pragma unroll
+    for (int off = 1; off <= 4; off <<= 1) {
+        Xf Y = xf_shfl_up(X, off);
+        if (lane >= 1 && lane < NB && lane - off >= ss) X = xf_compose(Y, X);
+    }
+    { Xf Y = xf_shfl(X, 3); if (lane >= 9 && lane <= 13) X = xf_compose(Y, X); }
+    { Xf Y = xf_shfl(X, 0); if (lane >= 1 && lane < NB) X = xf_compose(Y, X); }
+    return X;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dynamics: builds H (joint-space inertia, common frame) and its LDL^T in shared memory, returns the
+// unconstrained generalised acceleration in lane = dof layout.
+//   in : quat[4] (all lanes), q_dof, v_dof (lane = dof: 0..2 base angular, 3..5 base linear, 6.. hinges),
+//        tau_dof (hinge torque for lanes 6..26, else 0)
+//   out: acc (lane = dof);  W.u.s.H holds L (unit lower, row stride HS), W.dinv holds 1/D
+//        W.S holds the hinge motion vectors, W.foot the foot body poses
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dynamics_warp(const DevModel& M, WarpSmem& W, const float* quat, float q_dof, float v_dof,
+                                               float tau_dof, int lane, float* dbg) {
+    const int ss = seg_start(lane), se = seg_end(lane);
+    const bool isb = lane < NB, isj = lane >= 1 && lane < NB;
+    Xf X = fk_warp(M, quat, q_dof, lane);
+    // hinge motion vector S = (a ; o x a)
+    float S[6] = { 0, 0, 0, 0, 0, 0 };
+    if (isj) { matvec3(X.R, M.axis[lane], S); cross3(X.p, S, S + 3); }
+    if (isb) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) W.S[lane][i] = S[i];
+    }
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+        if (lane == M.foot_body[f]) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) W.foot[f][i] = X.R[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) W.foot[f][9 + i] = X.p[i];
+        }
+    // rigid-body inertia about the common origin: m, h = m c, Ibar (xx yy zz xy xz yz)
+    float m = 0, h[3] = { 0, 0, 0 }, I[6] = { 0, 0, 0, 0, 0, 0 };
+    if (isb) {
+        m = M.mass[lane];
+        float c[3]; matvec3(X.R, M.com[lane], c);
+        c[0] += X.p[0]; c[1] += X.p[1]; c[2] += X.p[2];
+        const float* in = M.inertia[lane];
+        float Il[9] = { in[0], in[3], in[4], in[3], in[1], in[5], in[4], in[5], in[2] }, T[9], Iw[9], Rt[9];
+        matmul3(X.R, Il, T);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) Rt[3 * i + j] = X.R[3 * j + i];
+        matmul3(T, Rt, Iw);
+        float cc = dot3(c, c);
+        I[0] = Iw[0] + m * (cc - c[0] * c[0]); I[1] = Iw[4] + m * (cc - c[1] * c[1]); I[2] = Iw[8] + m * (cc - c[2] * c[2]);
+        I[3] = Iw[1] - m * c[0] * c[1]; I[4] = Iw[2] - m * c[0] * c[2]; I[5] = Iw[5] - m * c[1] * c[2];
+        h[0] = m * c[0]; h[1] = m * c[1]; h[2] = m * c[2];
+    }
+    // composite inertia of each subtree
+    float mc = subtree_sum(m, lane, se), hc[3], Ic[6];
+#pragma unroll
+    for (int i = 0; i < 3; i++) hc[i] = subtree_sum(h[i], lane, se);
+#pragma unroll
+    for (int i = 0; i < 6; i++) Ic[i] = subtree_sum(I[i], lane, se);
+
+    // ---- H (composite rigid body algorithm) ----
+    float* H = W.u.s.H;
+    for (int i = lane; i < ND * HS; i += 32) H[i] = 0.f;
+    __syncwarp();
+    if (isj) {
+        // F = Ic * S : n = Ibar a + h x l ; f = m l - h x a
+        float F[6], t[3];
+        F[0] = Ic[0] * S[0] + Ic[3] * S[1] + Ic[4] * S[2];
+        F[1] = Ic[3] * S[0] + Ic[1] * S[1] + Ic[5] * S[2];
+        F[2] = Ic[4] * S[0] + Ic[5] * S[1] + Ic[2] * S[2];
+        cross3(hc, S + 3, t); F[0] += t[0]; F[1] += t[1]; F[2] += t[2];
+        cross3(hc, S, t);
+        F[3] = mc * S[3] - t[0]; F[4] = mc * S[4] - t[1]; F[5] = mc * S[5] - t[2];
+        int d = 5 + lane;
+        float hdd = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) hdd += S[i] * F[i];
+        H[d * HS + d] = hdd;
+        int j = lane;
+        // parents: chain neighbours except at the three branch points
+        for (int it = 0; it < 8; it++) {
+            j = (j == 9) ? 3 : ((j == 14 || j == 18 || j == 1) ? 0 : j - 1);
+            if (j < 1) break;
+            float v = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) v += W.S[j][i] * F[i];
+            H[d * HS + 5 + j] = v; H[(5 + j) * HS + d] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { H[i * HS + d] = F[i]; H[d * HS + i] = F[i]; }
+    }
+    if (lane == 0) {
+        H[0 * HS + 0] = Ic[0]; H[1 * HS + 1] = Ic[1]; H[2 * HS + 2] = Ic[2];
+        H[0 * HS + 1] = H[1 * HS + 0] = Ic[3]; H[0 * HS + 2] = H[2 * HS + 0] = Ic[4]; H[1 * HS + 2] = H[2 * HS + 1] = Ic[5];
+        H[3 * HS + 3] = H[4 * HS + 4] = H[5 * HS + 5] = mc;
+        // angular rows x linear cols = [h]x ; linear rows x angular cols = -[h]x
+        H[0 * HS + 4] = -hc[2]; H[0 * HS + 5] = hc[1]; H[1 * HS + 3] = hc[2]; H[1 * HS + 5] = -hc[0]; H[2 * HS + 3] = -hc[1]; H[2 * HS + 4] = hc[0];
+        H[4 * HS + 0] = -hc[2]; H[5 * HS + 0] = hc[1]; H[3 * HS + 1] = hc[2]; H[5 * HS + 1] = -hc[0]; H[3 * HS + 2] = -hc[1]; H[4 * HS + 2] = hc[0];
+    }
+    __syncwarp();
+
+    // ---- bias forces (recursive Newton-Euler with zero generalised acceleration, gravity as base acceleration) ----
+    float qd_b = shfl(v_dof, (lane + 5) & 31);      // hinge rate of body `lane`
+    float wb[3], vb[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { wb[i] = shfl(v_dof, i); vb[i] = shfl(v_dof, 3 + i); }
+    float vel[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float contrib = isj ? S[i] * qd_b : 0.f;
+        if (lane == 0) contrib = i < 3 ? wb[i] : vb[i - 3];
+        vel[i] = tree_prefix(contrib, lane, ss);
+    }
+    float acc6[6];
+    {
+        float t6[6] = { 0, 0, 0, 0, 0, 0 };
+        if (isj) {
+            // (v x_m S) qd : angular w x a ; linear w x l + v x a
+            float c1[3], c2[3], c3[3];
+            cross3(vel, S, c1); cross3(vel, S + 3, c2); cross3(vel + 3, S, c3);
+#pragma unroll
+            for (int i = 0; i < 3; i++) { t6[i] = c1[i] * qd_b; t6[3 + i] = (c2[i] + c3[i]) * qd_b; }
+        }
+        if (lane == 0) {
+            float c[3]; cross3(wb, vb, c);
+            t6[3] = -c[0]; t6[4] = -c[1]; t6[5] = -c[2] + M.gravity;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc6[i] = tree_prefix(t6[i], lane, ss);
+    }
+    float f6[6];
+    {
+        // f = I a + v x* (I v) with the body's own inertia
+        float Iv[6], Ia[6], t[3];
+        auto apply = [&](const float* x, float* y) {
+            y[0] = I[0] * x[0] + I[3] * x[1] + I[4] * x[2];
+            y[1] = I[3] * x[0] + I[1] * x[1] + I[5] * x[2];
+            y[2] = I[4] * x[0] + I[5] * x[1] + I[2] * x[2];
+            cross3(h, x + 3, t); y[0] += t[0]; y[1] += t[1]; y[2] += t[2];
+            cross3(h, x, t);
+            y[3] = m * x[3] - t[0]; y[4] = m * x[4] - t[1]; y[5] = m * x[5] - t[2];
+        };
+        apply(vel, Iv); apply(acc6, Ia);
+        float c1[3], c2[3], c3[3];
+        cross3(vel, Iv, c1); cross3(vel + 3, Iv + 3, c2); cross3(vel, Iv + 3, c3);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { f6[i] = Ia[i] + c1[i] + c2[i]; f6[3 + i] = Ia[3 + i] + c3[i]; }
+        if (!isb) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) f6[i] = 0.f;
+        }
+    }
+    float Fs[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) Fs[i] = subtree_sum(f6[i], lane, se);
+    float Cb = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) Cb += S[i] * Fs[i];
+    // move to lane = dof: base rows from lane 0's Fs, hinge rows from lane dof-5
+    float rhs = shfl(Cb, (lane + 27) & 31);       // lane d reads body d-5
+#pragma unroll
+    for (int i = 0; i < 6; i++) { float t = shfl(Fs[i], 0); if (lane == i) rhs = t; }
+    float Cdof = rhs;
+    rhs = tau_dof - rhs;
+    if (lane >= ND) rhs = 0.f;
+
+    // ---- LDL^T, lane i owns row i ----
+    float Hr[ND];
+#pragma unroll
+    for (int j = 0; j < ND; j++) Hr[j] = lane < ND ? H[lane * HS + j] : (j == lane ? 1.f : 0.f);
+    if (dbg) {
+        if (lane < ND) {
+            for (int j = 0; j < ND; j++) dbg[DBG_H + lane * ND + j] = Hr[j];
+            dbg[DBG_C + lane] = Cdof;
+        }
+    }
+    float myDinv = 1.f;
+#pragma unroll
+    for (int k = 0; k < ND; k++) {
+        float dk = shfl(Hr[k], k);
+        float inv = 1.f / dk;
+        if (lane == k) myDinv = inv;
+        float lik = Hr[k] * inv;
+#pragma unroll
+        for (int j = k + 1; j < ND; j++) {
+            float hkj = shfl(Hr[j], k);
+            if (lane > k) Hr[j] -= lik * hkj;
+        }
+        if (lane > k) Hr[k] = lik;
+    }
+    if (lane < ND) {
+#pragma unroll
+        for (int j = 0; j < ND; j++) H[lane * HS + j] = Hr[j];
+    }
+    W.dinv[lane] = myDinv;
+    __syncwarp();
+    // solve H acc = rhs
+    float y = rhs;
+#pragma unroll
+    for (int k = 0; k < ND - 1; k++) { float yk = shfl(y, k); if (lane > k && lane < ND) y -= Hr[k] * yk; }
+    y *= myDinv;
+#pragma unroll 1
+    for (int k = ND - 1; k >= 1; k--) { float xk = shfl(y, k); if (lane < k) y -= H[k * HS + lane] * xk; }
+    return lane < ND ? y : 0.f;
+}
+
+// back-substitution L^T x = u (lane = dof)
+__device__ __forceinline__ float solve_lt(const WarpSmem& W, float u, int lane) {
+    const float* H = W.u.s.H;
+#pragma unroll 1
+    for (int k = ND - 1; k >= 1; k--) { float xk = shfl(u, k); if (lane < k) u -= H[k * HS + lane] * xk; }
+    return u;
+}
+
+__device__ __forceinline__ void plane_space(const float* n, float* p, float* q) {
+    if (fabsf(n[2]) > 0.70710678f) {
+        float a = n[1] * n[1] + n[2] * n[2], k = rsqrtf(a);
+        p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+        q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        float a = n[0] * n[0] + n[1] * n[1], k = rsqrtf(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+        q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// position integration (btMultiBody::stepPositionsMultiDof): exponential map for the base orientation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void integrate_warp(const DevModel& M, float* quat, float& q_dof, float vnew, float* dpos, int lane) {
+    const float hdt = M.dt;
+    float w[3], vl[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { w[i] = shfl(vnew, i); vl[i] = shfl(vnew, 3 + i); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) dpos[i] += vl[i] * hdt;
+    float ang = sqrtf(dot3(w, w));
+    if (ang * hdt > 0.78539816f) ang = 0.78539816f / hdt;
+    float f = ang < 0.001f ? 0.5f * hdt - hdt * hdt * hdt * 0.020833333333f * ang * ang : sinf(0.5f * ang * hdt) / ang;
+    float dq[4] = { w[0] * f, w[1] * f, w[2] * f, cosf(0.5f * ang * hdt) }, rq[4];
+    rq[0] = dq[3] * quat[0] + dq[0] * quat[3] + dq[1] * quat[2] - dq[2] * quat[1];
+    rq[1] = dq[3] * quat[1] - dq[0] * quat[2] + dq[1] * quat[3] + dq[2] * quat[0];
+    rq[2] = dq[3] * quat[2] + dq[0] * quat[1] - dq[1] * quat[0] + dq[2] * quat[3];
+    rq[3] = dq[3] * quat[3] - dq[0] * quat[0] - dq[1] * quat[1] - dq[2] * quat[2];
+    float nn = rsqrtf(rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) quat[i] = rq[i] * nn;
+    if (lane >= 6 && lane < ND) q_dof += vnew * hdt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one physics substep.  State in registers: quat (all lanes), q_dof / v_dof (lane = dof), dpos =
+// displacement of the base since the start of the control step (all lanes), warm (lane = candidate slot).
+// Returns the per-foot contact flags of this substep's collision pass (bit f).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, float* quat, float& q_dof, float& v_dof,
+                                            float tau_dof, float* dpos, float& warm, int lane, float* dbg) {
+    const float hdt = M.dt;
+    float acc = dynamics_warp(M, W, quat, q_dof, v_dof, tau_dof, lane, dbg);
+    float vs = v_dof + hdt * acc;
+    vs = fminf(fmaxf(vs, -M.max_coord_vel), M.max_coord_vel);
+    if (lane >= ND) vs = 0.f;
+
+    // ---- collision: lane = (capsule, plank slot, segment end) ----
+    bool active = false; float depth = 0.f, cn[3] = { 0, 0, 0 }, cx[3] = { 0, 0, 0 };
+    const int cap = lane >> 3, slot = (lane >> 1) & 3, endp = lane & 1;
+    const int cbody = M.col_body[cap];
+    {
+        const float* st = W.stone[slot];
+        if (st[12] != 0.f) {
+            const float* fp = W.foot[M.col_foot[cap]];
+            float p0[3], p1[3], a[3], b[3], t[3];
+            matvec3(fp, M.col_p0[cap], t);
+#pragma unroll
+            for (int i = 0; i < 3; i++) p0[i] = fp[9 + i] + t[i] + dpos[i] - st[i];
+            matvec3(fp, M.col_p1[cap], t);
+#pragma unroll
+            for (int i = 0; i < 3; i++) p1[i] = fp[9 + i] + t[i] + dpos[i] - st[i];
+            matTvec3(st + 3, p0, a); matTvec3(st + 3, p1, b);
+            float t0 = 0.f, t1 = 1.f; bool empty = false;
+#pragma unroll
+            for (int ax = 0; ax < 2; ax++) {
+                float d = b[ax] - a[ax], hh = M.stone_half[ax];
+                if (fabsf(d) < 1e-12f) { if (fabsf(a[ax]) > hh) empty = true; }
+                else {
+                    float ta = (-hh - a[ax]) / d, tb = (hh - a[ax]) / d;
+                    if (ta > tb) { float s = ta; ta = tb; tb = s; }
+                    t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+                }
+            }
+            if (empty || t0 > t1) { t0 = 0.f; t1 = 1.f; }
+            if (!(endp == 1 && t1 - t0 < 1e-6f)) {
+                float tt = endp ? t1 : t0, s[3], q[3], nl[3], dist;
+                bool inside = true;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    s[i] = a[i] + tt * (b[i] - a[i]);
+                    float hh = M.stone_half[i];
+                    q[i] = fminf(fmaxf(s[i], -hh), hh);
+                    if (q[i] != s[i]) inside = false;
+                }
+                if (!inside) {
+                    float d[3] = { s[0] - q[0], s[1] - q[1], s[2] - q[2] };
+                    dist = sqrtf(dot3(d, d));
+                    float inv = 1.f / dist;
+                    nl[0] = d[0] * inv; nl[1] = d[1] * inv; nl[2] = d[2] * inv;
+                } else {
+                    int ax = 0; float best = 1e30f;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) { float mm = M.stone_half[i] - fabsf(s[i]); if (mm < best) { best = mm; ax = i; } }
+                    nl[0] = nl[1] = nl[2] = 0.f;
+                    float sg = (ax == 0 ? s[0] : (ax == 1 ? s[1] : s[2])) >= 0.f ? 1.f : -1.f;
+                    if (ax == 0) nl[0] = sg; else if (ax == 1) nl[1] = sg; else nl[2] = sg;
+                    dist = -best;
+                }
+                float r = M.col_radius[cap];
+                depth = dist - r;
+                if (depth < M.contact_breaking) {
+                    active = true;
+                    matvec3(st + 3, nl, cn);
+                    float sw[3]; matvec3(st + 3, s, sw);
+                    // contact point on the robot, relative to the CURRENT base origin
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cx[i] = sw[i] + st[i] - dpos[i] - r * cn[i];
+                }
+            }
+        }
+    }
+    unsigned amask = __ballot_sync(FULL, active);
+    if (__popc(amask) > MAXC) {          // keep the deepest MAXC (ties by slot)
+        int rank = 0;
+        for (int mlane = 0; mlane < 32; mlane++) {
+            float od = shfl(depth, mlane);
+            bool oa = (amask >> mlane) & 1;
+            if (oa && (od < depth || (od == depth && mlane < lane))) rank++;
+        }
+        active = active && rank < MAXC;
+        amask = __ballot_sync(FULL, active);
+    }
+    const int nc = __popc(amask);
+    const int cidx = __popc(amask & ((1u << lane) - 1u));
+    int cflags = 0;
+    if (amask & 0x0000ffffu) cflags |= 1 << M.col_foot[0];
+    if (amask & 0xffff0000u) cflags |= 1 << M.col_foot[2];
+    if (dbg) {
+        float* d = dbg + DBG_CAND + lane * 8;
+        d[0] = active ? 1.f : 0.f; d[1] = depth; d[2] = cn[0]; d[3] = cn[1]; d[4] = cn[2];
+        d[5] = cx[0]; d[6] = cx[1]; d[7] = cx[2];
+    }
+
+    // ---- violated hinge limits (lane = dof) ----
+    int lviol = 0; float lpen = 0.f;
+    if (lane >= 6 && lane < ND) {
+        float plo = q_dof - M.q_lo[lane - 6], phi = M.q_hi[lane - 6] - q_dof;
+        if (plo <= 0.f) { lviol = 1; lpen = plo; } else if (phi <= 0.f) { lviol = 2; lpen = phi; }
+    }
+    unsigned lmask = __ballot_sync(FULL, lviol != 0);
+    const int lidx = __popc(lmask & ((1u << lane) - 1u));
+    const int nl = min(__popc(lmask), MAXL);
+    const int nr = nl + 3 * nc;
+
+    float dv = 0.f;          // constraint velocity change (lane = dof)
+    float newwarm = 0.f;
+    if (nr > 0) {
+        // publish row definitions
+        if (lviol && lidx < MAXL) { W.lim[lidx][0] = (float)(lane - 6); W.lim[lidx][1] = lviol == 1 ? 1.f : -1.f; W.lim[lidx][2] = lpen; }
+        if (active) {
+            float* c = W.con[cidx];
+            c[0] = cn[0]; c[1] = cn[1]; c[2] = cn[2]; c[3] = cx[0]; c[4] = cx[1]; c[5] = cx[2];
+            c[6] = depth; c[7] = (float)cbody; c[8] = (float)lane; c[9] = warm;
+        }
+        if (lane < ND) W.vec[lane] = vs;
+        __syncwarp();
+
+        // ---- lane = row: Jacobian row, z = L^-1 J^T ----
+        const int r = lane;
+        float z[ND];
+#pragma unroll
+        for (int k = 0; k < ND; k++) z[k] = 0.f;
+        int rtype = -1;      // 0 limit, 1 normal, 2/3 friction
+        int nidx = -1; float pen = 0.f, lam = 0.f;
+        if (r < nl) {
+            rtype = 0;
+            int hj = (int)W.lim[r][0]; float dir = W.lim[r][1]; pen = W.lim[r][2];
+#pragma unroll
+            for (int k = 6; k < ND; k++) z[k] = (k - 6 == hj) ? dir : 0.f;
+        } else if (r < nr) {
+            int c, a;
+            if (r < nl + nc) { c = r - nl; a = 0; } else { c = (r - nl - nc) >> 1; a = 1 + ((r - nl - nc) & 1); nidx = nl + c; }
+            rtype = 1 + a;
+            const float* cd = W.con[c];
+            float n[3] = { cd[0], cd[1], cd[2] }, x[3] = { cd[3], cd[4], cd[5] }, dir[3], t1[3], t2[3];
+            plane_space(n, t1, t2);
+#pragma unroll
+            for (int i = 0; i < 3; i++) dir[i] = a == 0 ? n[i] : (a == 1 ? t1[i] : t2[i]);
+            pen = cd[6]; if (a == 0) lam = cd[9] * M.warmstart;
+            float wr[3]; cross3(x, dir, wr);
+            z[0] = wr[0]; z[1] = wr[1]; z[2] = wr[2]; z[3] = dir[0]; z[4] = dir[1]; z[5] = dir[2];
+            int mask = M.anc_mask[(int)cd[7]];
+#pragma unroll
+            for (int i = 1; i < NB; i++) {
+                const float* Si = W.S[i];
+                float v = Si[0] * wr[0] + Si[1] * wr[1] + Si[2] * wr[2] + Si[3] * dir[0] + Si[4] * dir[1] + Si[5] * dir[2];
+                z[5 + i] = ((mask >> i) & 1) ? v : 0.f;
+            }
+        }
+        // relative velocity along the row before the solve: J v*
+        float rel = 0.f;
+#pragma unroll
+        for (int k = 0; k < ND; k++) rel += z[k] * W.vec[k];
+        // forward substitution with the unit lower factor (broadcast reads of L)
+        const float* L = W.u.s.H;
+#pragma unroll
+        for (int k = 0; k < ND - 1; k++) {
+            float zk = z[k];
+#pragma unroll
+            for (int i = k + 1; i < ND; i++) z[i] -= L[i * HS + k] * zk;
+        }
+        float* Z = W.u.s.Z;
+#pragma unroll
+        for (int k = 0; k < ND; k++) Z[r * ZS + k] = z[k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < ND; k++) z[k] *= W.dinv[k];       // w = D^-1 z
+        // Delassus row: A[r][s] = w_r . z_s
+        float* A = W.u.s.A;
+        float diag = 0.f;
+        for (int s = 0; s < nr; s++) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < ND; k++) a += z[k] * Z[s * ZS + k];
+            A[r * AS + s] = a;
+            if (s == r) diag = a;
+        }
+        // row constants (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint / btMultiBodyJointLimitConstraint)
+        float invD = 0.f, rhs = 0.f, cfmt = 0.f, lo = 0.f, hi = 0.f;
+        if (rtype == 0) {
+            invD = 1.f / diag;
+            rhs = (-pen * M.erp_limit / hdt - rel) * invD;
+            hi = M.limit_max_impulse;
+        } else if (rtype >= 1) {
+            invD = 1.f / (diag + M.cfm_contact);
+            cfmt = M.cfm_contact * invD;
+            if (rtype == 1) {
+                float p = pen + M.linear_slop, poserr = 0.f, velerr = -rel;
+                if (p > 0.f) velerr -= p / hdt; else poserr = -p * M.erp_contact / hdt;
+                rhs = (poserr + velerr) * invD;
+                hi = 1e10f;
+            } else rhs = -rel * invD;
+        }
+        __syncwarp();
+        // overwrite Z with w for the final velocity update
+#pragma unroll
+        for (int k = 0; k < ND; k++) Z[r * ZS + k] = z[k];
+        // warm start: acc_r = sum_s A[r][s] lam_s
+        float jdv = 0.f;
+        for (int s = nl; s < nl + nc; s++) { float ls = shfl(lam, s); jdv += A[r * AS + s] * ls; }
+        if (dbg) {
+            dbg[DBG_ROWS + 0] = (float)nl; dbg[DBG_ROWS + 1] = (float)nc;
+            float* d = dbg + DBG_ROWS + 4 + lane * 6;
+            d[0] = (float)rtype; d[1] = invD; d[2] = rhs; d[3] = rel; d[4] = diag; d[5] = lam;
+            for (int s = 0; s < 32; s++) dbg[DBG_ROWS + 4 + 32 * 6 + lane * 32 + s] = (s < nr && lane < nr) ? A[r * AS + s] : 0.f;
+        }
+        // ---- projected Gauss-Seidel in constraint space (btMultiBodyConstraintSolver::solveSingleIteration order) ----
+        const int nsrc = nidx >= 0 ? nidx : lane;
+        const float mu = M.friction;
+        for (int it = 0; it < M.n_iters; it++) {
+            for (int s = 0; s < nr; s++) {
+                int rr = s < nl ? ((it & 1) ? s : nl - 1 - s) : s;
+                float ln = shfl(lam, nsrc);
+                float dl = 0.f;
+                if (lane == rr) {
+                    float lo_ = lo, hi_ = hi; bool skip = false;
+                    if (nidx >= 0) { if (!(ln > 0.f)) skip = true; lo_ = -mu * ln; hi_ = mu * ln; }
+                    if (!skip) {
+                        dl = rhs - lam * cfmt - jdv * invD;
+                        float sum = lam + dl;
+                        if (sum < lo_) { dl = lo_ - lam; sum = lo_; } else if (sum > hi_) { dl = hi_ - lam; sum = hi_; }
+                        lam = sum;
+                    }
+                }
+                dl = shfl(dl, rr);
+                jdv += A[r * AS + rr] * dl;
+            }
+        }
+        if (dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
+        // ---- velocity update: dv = L^-T sum_r w_r lam_r ----
+        float u = 0.f;
+        for (int s = 0; s < nr; s++) { float ls = shfl(lam, s); if (lane < ND) u += Z[s * ZS + lane] * ls; }
+        dv = solve_lt(W, u, lane);
+        // warm-start cache: candidate lane reads its normal row's impulse
+        float lw = shfl(lam, (nl + cidx) & 31);
+        newwarm = active ? lw : 0.f;
+        __syncwarp();
+    }
+    warm = newwarm;
+    float vnew = vs + dv;
+    vnew = fminf(fmaxf(vnew, -M.max_coord_vel), M.max_coord_vel);
+    if (lane >= ND) vnew = 0.f;
+    v_dof = vnew;
+
+    integrate_warp(M, quat, q_dof, vnew, dpos, lane);
+    return cflags;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MT19937 (numpy legacy RandomState) -- warp-cooperative on the env's state in global memory
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+__device__ __forceinline__ void mt_twist_warp(uint32_t* mt, int lane) {
+    // word k needs old mt[k+1] and mt[(k+397)%624] (old for k < 227, already-new afterwards):
+    // three dependency-free sweeps + the last word.  Each sweep reads everything before it writes.
+    const int lo[3] = { 0, 227, 454 }, hi[3] = { 227, 454, 623 };
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ph++) {
+        uint32_t tmp[8]; int cnt = 0;
+        for (int k = lo[ph] + lane; k < hi[ph]; k += 32) tmp[cnt++] = mt_mix(mt[k], mt[k + 1], mt[(k + 397) % 624]);
+        __syncwarp();
+        cnt = 0;
+        for (int k = lo[ph] + lane; k < hi[ph]; k += 32) mt[k] = tmp[cnt++];
+        __syncwarp();
+    }
+    if (lane == 0) mt[623] = mt_mix(mt[623], mt[0], mt[396]);
+    __syncwarp();
+}
+__device__ __forceinline__ double mt_make_double(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+// draw `count` doubles into out[] (out == nullptr discards them).  pos is warp-uniform.
+__device__ __forceinline__ void mt_doubles_warp(uint32_t* mt, int& pos, double* out, int count, int lane) {
+    int i = 0;
+    while (i < count) {
+        if (pos >= 624) { mt_twist_warp(mt, lane); pos = 0; }
+        int m = min(count - i, (624 - pos) / 2);
+        if (out)
+            for (int t = lane; t < m; t += 32)
+                out[i + t] = mt_make_double(mt_temper(mt[pos + 2 * t]), mt_temper(mt[pos + 2 * t + 1]));
+        i += m; pos += 2 * m;
+        if (i < count && pos == 623) {
+            uint32_t a = mt_temper(mt[623]);
+            __syncwarp();
+            mt_twist_warp(mt, lane);
+            uint32_t b = mt_temper(mt[0]);
+            pos = 1;
+            if (out && lane == 0) out[i] = mt_make_double(a, b);
+            i++;
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ double mt_one_double_warp(uint32_t* mt, int& pos, double* scratch, int lane) {
+    mt_doubles_warp(mt, pos, scratch, 1, lane);
+    return scratch[0];
+}
+
+// pybullet.getEulerFromQuaternion
+__device__ __forceinline__ void quat_to_rpy(const float* q, float* rpy) {
+    float sqx = q[0] * q[0], sqy = q[1] * q[1], sqz = q[2] * q[2], squ = q[3] * q[3];
+    float sarg = -2.f * (q[0] * q[2] - q[3] * q[1]);
+    const float HPI = 1.57079632679489662f;
+    if (sarg <= -0.99999f) { rpy[0] = 0; rpy[1] = -HPI; rpy[2] = 2 * atan2f(q[0], -q[1]); }
+    else if (sarg >= 0.99999f) { rpy[0] = 0; rpy[1] = HPI; rpy[2] = 2 * atan2f(-q[0], q[1]); }
+    else {
+        rpy[0] = atan2f(2 * (q[1] * q[2] + q[3] * q[0]), squ - sqx - sqy + sqz);
+        rpy[1] = asinf(sarg);
+        rpy[2] = atan2f(2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz);
+    }
+}
+
+}  // namespace ssb

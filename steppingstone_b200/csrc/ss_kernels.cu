@@ -1,0 +1,1013 @@
+// ss_kernels.cu -- kernels + C-ABI of libss_b200.so (sm_100a).  See include/ss_env.h for the contract and
+// ss_device.cuh for the warp-level physics.  One warp steps one env through a whole control step:
+//   apply_action -> 4 x (dynamics, collision, rows, PGS, integrate) -> calc_state -> calc_env_state ->
+//   reward / done / Monitor / TimeLimit -> auto-reset (terrain generator on the env's MT19937 stream).
+// There is no CPU fallback: every entry point needs a CUDA device and fails with SS_ERR_CUDA otherwise.
+#include "ss_device.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace ssb {
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int BLOCK = 32 * WARPS_PER_BLOCK;
+
+struct alignas(16) BlockSmem {
+    DevModel M;
+    unsigned long long bar;
+    unsigned long long pad;
+    WarpSmem W[WARPS_PER_BLOCK];
+};
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy of the constant tables into shared memory (cp.async.bulk -> UBLKCP) + mbarrier wait
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_model(BlockSmem& B, const DevModel* gm) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&B.bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&B.M);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)sizeof(DevModel)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(gm), "r"((uint32_t)sizeof(DevModel)), "r"(bar) : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-env register context (all fields warp-uniform unless noted)
+// ---------------------------------------------------------------------------------------------
+struct Env {
+    double pos[3];
+    float quat[4];
+    float q_dof, v_dof, warm;            // lane = dof / candidate slot
+    double potential, walk[3], initial_z, ep_ret;
+    float feet_contact[2], cache_contact[2];
+    double feet_xyz[2][3];
+    int next_step, reached, mirrored, elapsed, ep_len, update_terrain, phantom_idx, started;
+    int mtpos, gmtpos;
+};
+
+// state the physics needs (kept in registers across the substeps)
+__device__ __forceinline__ void env_load_phys(const DevState& S, int e, int lane, Env& E) {
+    const float* sv = S.sv + (size_t)e * 64;
+    float a = sv[lane], b = sv[32 + lane];
+#pragma unroll
+    for (int i = 0; i < 4; i++) E.quat[i] = shfl(a, i);
+    E.q_dof = shfl(a, (lane + 30) & 31);            // hinge j sits at sv[4+j]; dof 6+j reads lane j+4
+    if (lane < 6 || lane >= ND) E.q_dof = 0.f;
+    E.v_dof = lane < ND ? b : 0.f;
+    E.warm = S.warm[(size_t)e * SS_NWARM + lane];
+#pragma unroll
+    for (int i = 0; i < 3; i++) E.pos[i] = S.pos[(size_t)e * 3 + i];
+    E.next_step = S.ints[(size_t)e * SS_NINT + SS_I_NEXT_STEP];
+}
+// bookkeeping scalars (loaded after the physics so they do not occupy registers during it)
+__device__ __forceinline__ void env_load_rest(const DevState& S, int e, int lane, Env& E) {
+    const double* sc = S.scal + (size_t)e * SS_NSCAL;
+    E.potential = sc[SS_S_POTENTIAL];
+    E.walk[0] = sc[SS_S_WALK_X]; E.walk[1] = sc[SS_S_WALK_Y]; E.walk[2] = sc[SS_S_WALK_Z];
+    E.initial_z = sc[SS_S_INITIAL_Z];
+    E.feet_contact[0] = (float)sc[SS_S_FEET_CONTACT0]; E.feet_contact[1] = (float)sc[SS_S_FEET_CONTACT1];
+#pragma unroll
+    for (int i = 0; i < 6; i++) E.feet_xyz[i / 3][i % 3] = sc[SS_S_FEET_X0 + i];
+    E.ep_ret = sc[SS_S_EP_RET];
+    E.cache_contact[0] = (float)sc[SS_S_CACHE_CONTACT0]; E.cache_contact[1] = (float)sc[SS_S_CACHE_CONTACT1];
+    const int* it = S.ints + (size_t)e * SS_NINT;
+    E.reached = it[SS_I_REACHED_COUNT]; E.mirrored = it[SS_I_MIRRORED];
+    E.elapsed = it[SS_I_ELAPSED]; E.ep_len = it[SS_I_EP_LEN]; E.update_terrain = it[SS_I_UPDATE_TERRAIN];
+    E.phantom_idx = it[SS_I_PHANTOM_IDX]; E.started = it[SS_I_STARTED];
+    const uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
+    E.mtpos = (int)mt[624]; E.gmtpos = (int)mt[SS_MT_WORDS + 624];
+}
+__device__ __forceinline__ void env_load(const DevState& S, int e, int lane, Env& E) {
+    env_load_phys(S, e, lane, E);
+    env_load_rest(S, e, lane, E);
+}
+
+__device__ __forceinline__ void env_store(const DevState& S, int e, int lane, const Env& E) {
+    float* sv = S.sv + (size_t)e * 64;
+    float qh = shfl(E.q_dof, (lane + 2) & 31);      // lane j+4 takes dof 6+j
+    float a = 0.f;
+    if (lane < 4) a = lane == 0 ? E.quat[0] : (lane == 1 ? E.quat[1] : (lane == 2 ? E.quat[2] : E.quat[3]));
+    else if (lane < 4 + NJ) a = qh;
+    sv[lane] = a;
+    sv[32 + lane] = lane < ND ? E.v_dof : 0.f;
+    S.warm[(size_t)e * SS_NWARM + lane] = E.warm;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) S.pos[(size_t)e * 3 + i] = E.pos[i];
+        double* sc = S.scal + (size_t)e * SS_NSCAL;
+        sc[SS_S_POTENTIAL] = E.potential;
+        sc[SS_S_WALK_X] = E.walk[0]; sc[SS_S_WALK_Y] = E.walk[1]; sc[SS_S_WALK_Z] = E.walk[2];
+        sc[SS_S_INITIAL_Z] = E.initial_z;
+        sc[SS_S_FEET_CONTACT0] = E.feet_contact[0]; sc[SS_S_FEET_CONTACT1] = E.feet_contact[1];
+#pragma unroll
+        for (int i = 0; i < 6; i++) sc[SS_S_FEET_X0 + i] = E.feet_xyz[i / 3][i % 3];
+        sc[SS_S_EP_RET] = E.ep_ret;
+        sc[SS_S_CACHE_CONTACT0] = E.cache_contact[0]; sc[SS_S_CACHE_CONTACT1] = E.cache_contact[1];
+        int* it = S.ints + (size_t)e * SS_NINT;
+        it[SS_I_NEXT_STEP] = E.next_step; it[SS_I_REACHED_COUNT] = E.reached; it[SS_I_MIRRORED] = E.mirrored;
+        it[SS_I_ELAPSED] = E.elapsed; it[SS_I_EP_LEN] = E.ep_len; it[SS_I_UPDATE_TERRAIN] = E.update_terrain;
+        it[SS_I_PHANTOM_IDX] = E.phantom_idx; it[SS_I_STARTED] = E.started;
+        uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
+        mt[624] = (uint32_t)E.mtpos; mt[SS_MT_WORDS + 624] = (uint32_t)E.gmtpos;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// env logic (each function cites the reference lines it follows; oracle/ss_oracle.c has the scalar twin)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double base_phi(const DevModel& M, int mirrored, int k) {
+    // walker3d_envs.py:824-827 / mike.py:345-348
+    double b = k == 0 ? -10.0 : (k == M.n_steps - 1 ? 10.0 : ((k & 1) ? 20.0 : -20.0));
+    return SS_DEG_D * b * (mirrored ? 1.0 : -1.0);
+}
+__device__ __forceinline__ double sgn_d(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+__device__ __forceinline__ double clip_dx(const DevModel& M, double dx) {
+    return sgn_d(dx) * fmin(fmax(fabs(dx), M.step_radius * 2.5), M.r_max);
+}
+
+// feet link COM positions (bullet_utils.py:94) at the current pose: warp-cooperative FK
+__device__ __forceinline__ void feet_positions(const DevModel& M, Env& E, int lane) {
+    Xf X = fk_warp(M, E.quat, E.q_dof, lane);
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        float t[3]; matvec3(X.R, M.foot_ref[f], t);
+        int b = M.foot_body[f];
+#pragma unroll
+        for (int i = 0; i < 3; i++) E.feet_xyz[f][i] = E.pos[i] + (double)shfl(X.p[i] + t[i], b);
+    }
+}
+
+// robots.py:304-365 WalkerBase.calc_state.  Writes robot_state[50] into W.vec (clipped to +-5) and returns
+// roll/pitch/yaw + joints_at_limit.  Contact flags are the previous step's (q1).
+__device__ __forceinline__ void calc_state(const DevModel& M, WarpSmem& W, const Env& E, int lane, float* rpy, int& jal,
+                                           bool& finite) {
+    quat_to_rpy(E.quat, rpy);
+    float ang = 0.f, spd = 0.f; bool at_limit = false;
+    if (lane >= 6 && lane < ND) {
+        int j = lane - 6;
+        float lo = M.q_lo[j], hi = M.q_hi[j];
+        ang = 2.f * (E.q_dof - 0.5f * (lo + hi)) / (hi - lo);          // bullet_utils.py:191-194
+        spd = 0.1f * E.v_dof;
+        at_limit = fabsf(ang) > 0.99f;
+    }
+    jal = __popc(__ballot_sync(FULL, at_limit));
+    float vx0 = shfl(E.v_dof, 3), vy0 = shfl(E.v_dof, 4), vz0 = shfl(E.v_dof, 5);
+    float s, c; sincosf(-rpy[2], &s, &c);
+    float more[6] = { (float)(E.pos[2] - E.initial_z), c * vx0 - s * vy0, s * vx0 + c * vy0, vz0, rpy[0], rpy[1] };
+    auto clip5 = [](float x) { return x < -5.f ? -5.f : (x > 5.f ? 5.f : x); };   // NaN passes through, as np.clip
+    __syncwarp();
+    if (lane < 6) W.vec[lane] = clip5(lane == 0 ? more[0] : lane == 1 ? more[1] : lane == 2 ? more[2] : lane == 3 ? more[3] : lane == 4 ? more[4] : more[5]);
+    else if (lane < ND) { W.vec[lane] = clip5(ang); W.vec[21 + lane] = clip5(spd); }
+    else if (lane < ND + 2) W.vec[48 + lane - ND] = clip5(E.feet_contact[lane - ND]);
+    __syncwarp();
+    bool ok = true;
+    if (lane < 25) ok = isfinite(W.vec[lane]) && isfinite(W.vec[25 + lane]);
+    finite = __all_sync(FULL, ok);
+}
+
+// walker3d_envs.py:910-924
+__device__ __forceinline__ double calc_potential(const DevModel& M, Env& E, double& dist) {
+    double dx = E.walk[0] - E.pos[0], dy = E.walk[1] - E.pos[1];
+    dist = sqrt(dx * dx + dy * dy);
+    return -dist / M.control_dt;
+}
+
+// walker3d_envs.py:798-810
+__device__ __forceinline__ void update_steps(const DevModel& M, const DevState& S, int e, const Env& E, int lane) {
+    int thr = M.rendered / 2;
+    if (E.next_step >= thr) {
+        int oldest = ((E.next_step - thr - 1) % M.rendered + M.rendered) % M.rendered;
+        int next = min(E.next_step - thr - 1 + M.rendered, M.n_steps - 1);
+        if (lane < 6) S.plank[((size_t)e * M.rendered + oldest) * 6 + lane] = S.terrain[((size_t)e * M.n_steps + next) * 6 + lane];
+    }
+    __syncwarp();
+}
+
+// walker3d_envs.py:961-999.  feet_xyz must be current.  Returns target_reached; foot_dist = planar distances.
+__device__ __forceinline__ bool calc_feet_state(const DevModel& M, const DevState& S, int e, Env& E, int lane, double* foot_dist) {
+    const double* p = S.terrain + ((size_t)e * M.n_steps + E.next_step) * 6;
+    double px = p[0], py = p[1], pz = p[2];
+    bool reached = false;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        E.feet_contact[i] = E.cache_contact[i] != 0.f ? 1.f : 0.f;
+        double dx = E.feet_xyz[i][0] - px, dy = E.feet_xyz[i][1] - py, dz = E.feet_xyz[i][2] - pz;
+        foot_dist[i] = sqrt(dx * dx + dy * dy);
+        if (E.feet_contact[i] != 0.f && (dx * dx + dy * dy + dz * dz) < 0.3) reached = true;
+    }
+    if (reached) {
+        E.reached++;
+        if (E.reached >= M.stop_frames) { E.next_step++; E.reached = 0; update_steps(M, S, e, E, lane); }
+        if (E.next_step >= M.n_steps) E.next_step--;
+    }
+    return reached;
+}
+
+// walker3d_envs.py:1046-1077; yaw is the base yaw of the last calc_state.  targets -> W.vec[50..59]
+__device__ __forceinline__ void delta_to_k_targets(const DevModel& M, const DevState& S, WarpSmem& W, int e, Env& E, float yaw, int lane) {
+    float out[10];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int idx = min(E.next_step + k, M.n_steps - 1);
+        const double* t = S.terrain + ((size_t)e * M.n_steps + idx) * 6;
+        double tx = t[0], ty = t[1], tz = t[2];
+        if (k == 1) { E.walk[0] = tx; E.walk[1] = ty; E.walk[2] = tz; }          // q8
+        float dx = (float)(tx - E.pos[0]), dy = (float)(ty - E.pos[1]), dz = (float)(tz - E.pos[2]);
+        float ang = atan2f(dy, dx) - yaw, dist = sqrtf(dx * dx + dy * dy), s, c;
+        sincosf(ang, &s, &c);
+        out[5 * k] = s * dist; out[5 * k + 1] = c * dist; out[5 * k + 2] = dz; out[5 * k + 3] = (float)t[4]; out[5 * k + 4] = (float)t[5];
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) W.vec[50 + i] = out[i];
+    }
+    __syncwarp();
+}
+
+// walker3d_envs.py:1245-1274 / mike.py:755-784
+__device__ __forceinline__ void set_next_next_step_location(const DevModel& M, const DevState& S, int e, const Env& E, int lane,
+                                                            double pitch, double yaw, double dr, double xt, double yt) {
+    const double* nx = S.terrain + ((size_t)e * M.n_steps + E.next_step) * 6;
+    int bci = (E.next_step + 1) % M.n_steps;
+    double bphi = base_phi(M, E.mirrored, bci), byaw = nx[3];
+    double sp, cp, sy, cy, sb, cb;
+    sincos(pitch, &sp, &cp); sincos(yaw + bphi, &sy, &cy); sincos(byaw, &sb, &cb);
+    double dx = clip_dx(M, dr * sp * cy), dy = dr * sp * sy;
+    double v[6] = { nx[0] + cb * dx - sb * dy, nx[1] + sb * dx + cb * dy, nx[2] + dr * cp, yaw + byaw, xt, yt };
+    __syncwarp();
+    if (lane == 0) {
+        double* t = S.terrain + ((size_t)e * M.n_steps + bci) * 6;
+#pragma unroll
+        for (int i = 0; i < 6; i++) t[i] = v[i];
+    }
+    __syncwarp();
+}
+
+// mike.py:660-692: RandomState.choice(p, size=1, replace=False) == one uniform + searchsorted(cdf, u, 'right')
+__device__ __forceinline__ void sample_next_next_step(const DevModel& M, const DevState& S, WarpSmem& W, int e, Env& E, int lane) {
+    uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
+    double u = mt_one_double_warp(mt, E.mtpos, W.u.d, lane);
+    int lo = 0, hi = S.n_cells;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < S.cdf[mid]) hi = mid; else lo = mid + 1; }
+    int idx = lo < S.n_cells ? lo : S.n_cells - 1;
+    const int g = SS_GRID;
+    int i4 = idx % g, i3 = (idx / g) % g, i2 = (idx / (g * g)) % g, i1 = (idx / (g * g * g)) % g, i0 = idx / (g * g * g * g);
+    set_next_next_step_location(M, S, e, E, lane, M.samples[1][i1] + SS_PI_D / 2, M.samples[0][i0], M.samples[2][i2],
+                                M.samples[3][i3], M.samples[4][i4]);
+}
+
+// walker3d_envs.py:1079-1093 / mike.py:589-603
+__device__ __forceinline__ void update_terrain_info(const DevModel& M, const DevState& S, WarpSmem& W, int e, Env& E, float yaw, int lane) {
+    int nn = E.next_step + 1;
+    if (M.use_sampler) sample_next_next_step(M, S, W, e, E, lane);
+    if (lane < 6) S.plank[((size_t)e * M.rendered + nn % M.rendered) * 6 + lane] = S.terrain[((size_t)e * M.n_steps + nn % M.n_steps) * 6 + lane];
+    __syncwarp();
+    delta_to_k_targets(M, S, W, e, E, yaw, lane);
+}
+
+// walker3d_envs.py:624-755 (W3D) / mike.py:167-276 (Mike).  Scratch: W.u.d (>= 13 * n_steps doubles).
+__device__ __forceinline__ void generate_step_placements(const DevModel& M, const DevState& S, WarpSmem& W, int e, Env& E, int lane) {
+    const int n = M.n_steps;
+    double* dr = W.u.d; double *dphi = dr + n, *dth = dr + 2 * n, *xt = dr + 3 * n, *yt = dr + 4 * n, *cphi = dr + 5 * n,
+            *X = dr + 6 * n, *Y = dr + 7 * n, *Z = dr + 8 * n, *U = dr + 9 * n, *YAW = dr + 10 * n, *PHI = dr + 11 * n;
+    uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
+    double* T = S.terrain + (size_t)e * n * 6;
+    const bool mike = M.terrain_mode == 1;
+    const double dr_lo = 0.65, dr_hi = mike ? 0.65 : 0.8, y0 = mike ? -10 * SS_DEG_D : 0.0, t0 = mike ? -20 * SS_DEG_D : 0.0;
+    __syncwarp();
+    mt_doubles_warp(mt, E.mtpos, dr, n, lane);
+    mt_doubles_warp(mt, E.mtpos, dphi, n, lane);
+    mt_doubles_warp(mt, E.mtpos, dth, n, lane);
+    mt_doubles_warp(mt, E.mtpos, xt, n, lane);
+    mt_doubles_warp(mt, E.mtpos, yt, n, lane);
+    for (int i = lane; i < n; i += 32) {
+        dr[i] = dr_lo + (dr_hi - dr_lo) * dr[i];
+        dphi[i] = y0 + (y0 - y0) * dphi[i];
+        dth[i] = 90 * SS_DEG_D + (90 * SS_DEG_D - 90 * SS_DEG_D) * dth[i];
+        xt[i] = t0 + (t0 - t0) * xt[i];
+        yt[i] = 0.0 + 0.0 * yt[i];
+        if (i < 3) {
+            dr[i] = i == 0 ? 0.0 : (i == 1 ? 0.8 : 0.75); dphi[i] = 0.0; dth[i] = SS_PI_D / 2; xt[i] = 0.0; yt[i] = 0.0;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) { double acc = 0; for (int i = 0; i < n; i++) { acc += dphi[i]; cphi[i] = acc; } }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        double bp = base_phi(M, E.mirrored, i), st, ct, sp, cp;
+        sincos(dth[i], &st, &ct); sincos(cphi[i] + bp, &sp, &cp);
+        double x_ = dr[i] * st * cp;
+        if (i >= 2) x_ = clip_dx(M, x_);
+        X[i] = x_; Y[i] = dr[i] * st * sp; Z[i] = dr[i] * ct;
+    }
+    __syncwarp();
+    const double min_z = M.step_radius * sin(M.tilt_limit_deg * SS_DEG_D) + 0.01;
+    if (lane == 0) {
+        double ax = 0, ay = 0, az = 0;
+        for (int i = 0; i < n; i++) {
+            ax += X[i]; ay += Y[i]; az += Z[i];
+            double* t = T + 6 * i;
+            t[0] = ax; t[1] = ay; t[2] = fmax(az + 0, min_z); t[3] = cphi[i]; t[4] = xt[i]; t[5] = yt[i];
+        }
+    }
+    __syncwarp();
+    // second pass: stones 3..n-1 are re-placed relative to their predecessor (walker3d_envs.py:700-755)
+    if (!mike) mt_doubles_warp(mt + SS_MT_WORDS, E.gmtpos, U + 2, n - 3, lane);      // global numpy stream (q7)
+    for (int i = 2 + lane; i < n - 1; i += 32) {
+        int bci = i + 1;
+        double bphi = base_phi(M, E.mirrored, bci);
+        double pitch = dth[bci], yaw = dphi[bci];
+        if (!mike) {
+            pitch = (i % 2 == 0) ? 120 * SS_DEG_D : 60 * SS_DEG_D;
+            if (U[i] < 0.2) pitch = 90 * SS_DEG_D;
+            if (M.terrain_mode == 2) pitch = 90 * SS_DEG_D;
+        }
+        double sp, cp, sy, cy;
+        sincos(pitch, &sp, &cp); sincos(yaw + bphi, &sy, &cy);
+        X[i] = clip_dx(M, dr[bci] * sp * cy); Y[i] = dr[bci] * sp * sy; Z[i] = dr[bci] * cp; YAW[i] = yaw;
+    }
+    __syncwarp();
+    if (lane == 0) { PHI[2] = cphi[2]; for (int i = 2; i < n - 1; i++) PHI[i + 1] = YAW[i] + PHI[i]; }
+    __syncwarp();
+    for (int i = 2 + lane; i < n - 1; i += 32) {
+        double sb, cb; sincos(PHI[i], &sb, &cb);
+        double dx = X[i], dy = Y[i];
+        X[i] = cb * dx + -sb * dy; Y[i] = sb * dx + cb * dy;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double x = T[12], y = T[13], z = T[14];
+        for (int i = 2; i < n - 1; i++) {
+            x = x + X[i]; y = y + Y[i]; z = z + Z[i];
+            double* t = T + 6 * (i + 1);
+            t[0] = x; t[1] = y; t[2] = z; t[3] = PHI[i + 1];
+            if (mike) t[4] = -20 * SS_DEG_D;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void write_obs(const WarpSmem& W, const Env& E, float* obs, int lane) {
+    float h = (float)(E.pos[2] - fmin(E.feet_xyz[0][2], E.feet_xyz[1][2]));                   // q6
+    float a = W.vec[lane], b = lane < 28 ? W.vec[32 + lane] : 0.f;
+    if (lane == 0) a = h;
+    obs[lane] = a;
+    if (lane < 28) obs[32 + lane] = b;
+}
+
+// Walker3DStepperEnv.reset walker3d_envs.py:812-867 / mike.py:333-388 + Walker3D.reset robots.py:581-618
+__device__ __forceinline__ void env_reset(const DevModel& M, const DevState& S, WarpSmem& W, int e, Env& E, float* obs, int lane) {
+    uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
+    E.reached = 0;
+    double u = mt_one_double_warp(mt, E.mtpos, W.u.d, lane);                  // robots.py:583 / :846 (q10)
+    E.mirrored = u < M.mirror_prob;
+    int j = lane - 6, src = j;
+    if (E.mirrored) {
+        if ((j >= 3 && j <= 7) || (j >= 13 && j <= 16)) src = j + (j <= 7 ? 5 : 4);
+        else if ((j >= 8 && j <= 12) || (j >= 17 && j <= 20)) src = j - (j <= 12 ? 5 : 4);
+    }
+    float q = 0.f;
+    if (j >= 0 && j < NJ) { q = M.init_q[src]; if (E.mirrored && (j == 0 || j == 2)) q = -q; }
+    E.q_dof = q; E.v_dof = 0.f;           // resetBasePositionAndOrientation zeroes both base velocities (oracle env_reset)
+#pragma unroll
+    for (int i = 0; i < 3; i++) E.pos[i] = M.init_pos[i];
+    E.quat[0] = E.quat[1] = E.quat[2] = 0.f; E.quat[3] = 1.f;
+    // WalkerBase.reset robots.py:433-439
+    E.feet_contact[0] = E.feet_contact[1] = 0.f;
+    E.initial_z = E.pos[2];
+    float rpy[3]; int jal; bool fin;
+    calc_state(M, W, E, lane, rpy, jal, fin);
+    // stale-state calc_feet_state (q2)
+    feet_positions(M, E, lane);
+    double fd[2];
+    calc_feet_state(M, S, e, E, lane, fd);
+    generate_step_placements(M, S, W, e, E, lane);
+    for (int i = lane; i < M.rendered * 6; i += 32) S.plank[(size_t)e * M.rendered * 6 + i] = S.terrain[(size_t)e * M.n_steps * 6 + i];
+    __syncwarp();
+    E.next_step = 1;
+    delta_to_k_targets(M, S, W, e, E, rpy[2], lane);
+    double dist; E.potential = calc_potential(M, E, dist);
+    write_obs(W, E, obs, lane);
+    E.phantom_idx = 0;
+    mt_doubles_warp(mt, E.mtpos, nullptr, 22 * M.n_phantoms, lane);           // walker3d_envs.py:859-862 (q11)
+    E.elapsed = 0; E.ep_ret = 0; E.ep_len = 0; E.update_terrain = 0; E.started = 1;
+}
+
+// stone boxes of the 4 candidate slots around next_step, relative to the step-start base position
+__device__ __forceinline__ void setup_stones(const DevModel& M, const DevState& S, WarpSmem& W, int e, const Env& E, int lane) {
+    if (lane < 4) {
+        int k = -1;
+        for (int kk = E.next_step - 2; kk <= E.next_step + 1; kk++) if (kk >= 0 && (kk & 3) == lane) k = kk;
+        float* st = W.stone[lane];
+        if (k < 0 || k > M.n_steps - 1) st[12] = 0.f;
+        else {
+            const double* pl = S.plank + ((size_t)e * M.rendered + k % M.rendered) * 6;
+            // getQuaternionFromEuler([x_tilt, y_tilt, phi]) : Rz(yaw) Ry(pitch) Rx(roll); bullet_objects.py:75-80 (q12)
+            double sr, cr, sp, cp, sy, cy;
+            sincos(pl[4], &sr, &cr); sincos(pl[5], &sp, &cp); sincos(pl[3], &sy, &cy);
+            double R[9] = { cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                            sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                            -sp, cp * sr, cp * cr };
+            double off = M.stone_box_off;
+            st[0] = (float)(pl[0] + R[2] * off - E.pos[0]);
+            st[1] = (float)(pl[1] + R[5] * off - E.pos[1]);
+            st[2] = (float)(pl[2] - (double)M.stone_com_z + R[8] * off - E.pos[2]);
+#pragma unroll
+            for (int i = 0; i < 9; i++) st[3 + i] = (float)R[i];
+            st[12] = 1.f;
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__global__ void __launch_bounds__(BLOCK) env_step_kernel(const DevModel* gm, DevState S, const float* __restrict__ act,
+                                                         float* __restrict__ obs, float* __restrict__ rew,
+                                                         uint8_t* __restrict__ done, uint8_t* __restrict__ timeout,
+                                                         float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int physics) {
+    BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
+    stage_model(B, gm);
+    const DevModel& M = B.M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= S.n) return;
+    WarpSmem& W = B.W[warp];
+    Env E; env_load_phys(S, e, lane, E);
+
+    // robots.py:289-293 apply_action (torque held over the control step) + MJCF joint damping torque
+    float a_raw = 0.f, tau = 0.f;
+    if (lane >= 6 && lane < ND) {
+        int j = lane - 6;
+        a_raw = act[(size_t)e * NJ + j];
+        float x = fminf(fmaxf(a_raw, -1.f), 1.f);
+        if (M.actuator_mode == 0) tau = M.tau_max[j] * x;
+        else {                                                                     // robots.py:486-493 (opt-in PD)
+            float lo = M.q_lo[j], hi = M.q_hi[j];
+            tau = M.pd_p[j] * (x - 2.f * (E.q_dof - 0.5f * (lo + hi)) / (hi - lo)) - M.pd_d[j] * E.v_dof;
+        }
+        tau -= M.damping[j] * E.v_dof;
+    }
+    int cflags = -1;
+    if (physics) {
+        setup_stones(M, S, W, e, E, lane);
+        float dpos[3] = { 0.f, 0.f, 0.f };
+        for (int s = 0; s < M.n_substeps; s++) {
+            float* dbg = (S.dbg && s == M.n_substeps - 1) ? S.dbg + (size_t)e * DBG_FLOATS : nullptr;
+            cflags = substep_warp(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg);
+            if (S.trace_q && s < 4) {
+                double* tq = S.trace_q + ((size_t)s * S.n + e) * SS_NQ;
+                double* tv = S.trace_qd + ((size_t)s * S.n + e) * ND;
+                if (lane < 3) tq[lane] = E.pos[lane] + (double)(lane == 0 ? dpos[0] : lane == 1 ? dpos[1] : dpos[2]);
+                if (lane < 4) tq[3 + lane] = lane == 0 ? E.quat[0] : lane == 1 ? E.quat[1] : lane == 2 ? E.quat[2] : E.quat[3];
+                if (lane >= 6 && lane < ND) tq[1 + lane] = E.q_dof;
+                if (lane < ND) tv[lane] = E.v_dof;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) E.pos[i] += (double)dpos[i];
+    }
+    env_load_rest(S, e, lane, E);
+    if (cflags >= 0) { E.cache_contact[0] = (cflags & 1) ? 1.f : 0.f; E.cache_contact[1] = (cflags & 2) ? 1.f : 0.f; }
+
+    // ---- robot.calc_state + calc_env_state (walker3d_envs.py:875-903, 1026-1044) ----
+    float rpy[3]; int jal; bool finite;
+    calc_state(M, W, E, lane, rpy, jal, finite);
+    bool dn = !finite;
+    const int cur = E.next_step;
+    feet_positions(M, E, lane);
+    double fd[2];
+    bool reached = calc_feet_state(M, S, e, E, lane, fd);
+    // calc_base_reward walker3d_envs.py:926-959
+    double old_pot = E.potential, dist;
+    E.potential = calc_potential(M, E, dist);
+    float progress = (float)(E.potential - old_pot);
+    float posture = 0.f;
+    if (!(-0.2f < rpy[1] && rpy[1] < 0.4f)) posture = fabsf(rpy[1]);
+    if (!(-0.4f < rpy[0] && rpy[0] < 0.4f)) posture += fabsf(rpy[0]);
+    float m1 = 0.f, m2 = 0.f;
+    if (lane >= 6 && lane < ND) { m1 = fabsf(a_raw * 0.1f * E.v_dof); m2 = a_raw * a_raw; }      // unclipped action (q5)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { m1 += __shfl_xor_sync(FULL, m1, off); m2 += __shfl_xor_sync(FULL, m2, off); }
+    float energy = M.electricity_cost * (m1 / NJ) + M.stall_torque_cost * (m2 / NJ);
+    float joints_pen = M.joints_at_limit_cost * (float)jal;
+    float height = (float)(E.pos[2] - fmin(E.feet_xyz[0][2], E.feet_xyz[1][2]));
+    float tall = height > M.done_height ? 2.f : -1.f;
+    dn = dn || tall < 0.f;
+    // calc_step_reward walker3d_envs.py:1001-1024
+    float step_bonus = 0.f;
+    if (reached && E.reached == 1) {
+        step_bonus = 50.f * expf(-(float)fmin(fd[0], fd[1]) / 0.25f);
+        if (M.n_phantoms > 0 && E.next_step % 3 == 0) {                            // phantom.reset: 22 draws (q11)
+            mt_doubles_warp(S.mt + (size_t)e * 2 * SS_MT_WORDS, E.mtpos, nullptr, 22, lane);
+            E.phantom_idx = (E.phantom_idx + 1) % 20;
+        }
+    }
+    float target_bonus = (E.next_step == M.n_steps - 1 && dist < 0.15) ? 2.f : 0.f;
+    delta_to_k_targets(M, S, W, e, E, rpy[2], lane);
+    E.update_terrain = cur != E.next_step;
+    if (cur != E.next_step) { update_terrain_info(M, S, W, e, E, rpy[2], lane); double d2; E.potential = calc_potential(M, E, d2); }
+    float r = progress - energy;
+    r += step_bonus + target_bonus - 0.f;
+    r += tall - posture - joints_pen;
+    float* o = obs + (size_t)e * SS_OBS;
+    write_obs(W, E, o, lane);
+    if (!physics) {
+        if (lane == 0) { rew[e] = r; done[e] = dn ? 1 : 0; }
+        env_store(S, e, lane, E);
+        return;
+    }
+    // gym TimeLimit + TimeLimitMask envs_utils.py:59-69 + Monitor :130-153
+    E.elapsed++;
+    bool d = dn || E.elapsed >= M.max_episode_steps;
+    E.ep_ret += (double)r; E.ep_len++;
+    if (lane == 0) {
+        rew[e] = r; done[e] = d ? 1 : 0;
+        timeout[e] = (d && E.elapsed == M.max_episode_steps) ? 1 : 0;
+        ep_ret[e] = (float)(rint(E.ep_ret * 1e6) / 1e6); ep_len[e] = E.ep_len;
+    }
+    if (d) { __syncwarp(); env_reset(M, S, W, e, E, o, lane); }                     // envs_utils.py:646-649
+    env_store(S, e, lane, E);
+}
+
+__global__ void __launch_bounds__(BLOCK) env_reset_kernel(const DevModel* gm, DevState S, float* __restrict__ obs) {
+    BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
+    stage_model(B, gm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= S.n) return;
+    Env E; env_load(S, e, lane, E);
+    env_reset(B.M, S, B.W[warp], e, E, obs + (size_t)e * SS_OBS, lane);
+    env_store(S, e, lane, E);
+}
+
+// update_sample_prob's immediate re-sample (walker3d_envs.py:1317-1320): envs whose update_terrain flag is set
+__global__ void __launch_bounds__(BLOCK) resample_kernel(const DevModel* gm, DevState S) {
+    BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
+    stage_model(B, gm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= S.n) return;
+    Env E; env_load(S, e, lane, E);
+    if (E.update_terrain) {
+        float rpy[3]; quat_to_rpy(E.quat, rpy);
+        update_terrain_info(B.M, S, B.W[warp], e, E, rpy[2], lane);
+        env_store(S, e, lane, E);
+    }
+}
+
+// stand-alone forward-dynamics substep: q [N,28], qd [N,27], tau [N,21] f32 -> q, qd in place (524 B / env-substep)
+__global__ void __launch_bounds__(BLOCK) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
+                                                            const float* __restrict__ tau, int n) {
+    BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
+    stage_model(B, gm);
+    const DevModel& M = B.M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= n) return;
+    WarpSmem& W = B.W[warp];
+    float* qe = q + (size_t)e * SS_NQ; float* ve = qd + (size_t)e * ND;
+    float a = lane < SS_NQ ? qe[lane] : 0.f;
+    float quat[4], pos[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) pos[i] = shfl(a, i);
+#pragma unroll
+    for (int i = 0; i < 4; i++) quat[i] = shfl(a, 3 + i);
+    float q_dof = shfl(a, (lane + 1) & 31);          // dof 6+j reads q[7+j]
+    if (lane < 6 || lane >= ND) q_dof = 0.f;
+    float v_dof = lane < ND ? ve[lane] : 0.f;
+    float t = (lane >= 6 && lane < ND) ? tau[(size_t)e * NJ + lane - 6] : 0.f;
+    float acc = dynamics_warp(M, W, quat, q_dof, v_dof, t, lane, nullptr);
+    float vn = v_dof + M.dt * acc;
+    vn = fminf(fmaxf(vn, -M.max_coord_vel), M.max_coord_vel);
+    if (lane >= ND) vn = 0.f;
+    float dpos[3] = { 0.f, 0.f, 0.f };
+    integrate_warp(M, quat, q_dof, vn, dpos, lane);
+    float qh = shfl(q_dof, (lane + 31) & 31);
+    float out = 0.f;
+    if (lane < 3) out = (lane == 0 ? pos[0] + dpos[0] : lane == 1 ? pos[1] + dpos[1] : pos[2] + dpos[2]);
+    else if (lane < 7) out = lane == 3 ? quat[0] : lane == 4 ? quat[1] : lane == 5 ? quat[2] : quat[3];
+    else out = qh;
+    if (lane < SS_NQ) qe[lane] = out;
+    if (lane < ND) ve[lane] = vn;
+}
+
+// RolloutStorage.compute_returns(use_gae=True) -- algorithms/storage.py:59-71.  One thread per env, time scan.
+__global__ void gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const float* __restrict__ masks,
+                           const float* __restrict__ bad_masks, float* __restrict__ returns, int T, int N, float gamma, float lam) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float gae = 0.f, vnext = values[(size_t)T * N + i];
+    for (int t = T - 1; t >= 0; t--) {
+        float m = masks[(size_t)(t + 1) * N + i], bm = bad_masks[(size_t)(t + 1) * N + i], v = values[(size_t)t * N + i];
+        float delta = rewards[(size_t)t * N + i] + gamma * vnext * m - v;
+        gae = delta + gamma * lam * m * gae;
+        gae = gae * bm;
+        returns[(size_t)t * N + i] = gae + v;
+        vnext = v;
+    }
+}
+
+}  // namespace ssb
+
+// ===============================================================================================
+// host side: C-ABI
+// ===============================================================================================
+using namespace ssb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(SS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct ss_env {
+    int n = 0, device = 0, n_steps = 0, rendered = 0;
+    DevModel hm;
+    DevModel* dm = nullptr;
+    DevState S{};
+    double* cdf = nullptr;
+    int64_t launches = 0;
+    size_t smem = 0;
+    bool trace = false, debug = false;
+    // pinned staging for the host-buffer entry points
+    float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_epret = nullptr;
+    uint8_t *h_done = nullptr, *h_to = nullptr; int32_t* h_eplen = nullptr;
+    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_epret = nullptr;
+    uint8_t *d_done = nullptr, *d_to = nullptr; int32_t* d_eplen = nullptr;
+    cudaStream_t own = nullptr;
+};
+
+static void fill_model(DevModel& D, const ss_model& m, const ss_params& p) {
+    memset(&D, 0, sizeof D);
+    for (int i = 0; i < NB; i++) {
+        for (int k = 0; k < 3; k++) { D.anchor[i][k] = (float)m.anchor[i][k]; D.axis[i][k] = (float)m.axis[i][k]; D.com[i][k] = (float)m.com[i][k]; }
+        for (int k = 0; k < 9; k++) D.R0[i][k] = (float)m.R0[i][k];
+        for (int k = 0; k < 6; k++) D.inertia[i][k] = (float)m.inertia[i][k];
+        D.mass[i] = (float)m.mass[i];
+        int mask = 0;
+        for (int b = i; b >= 1; b = m.parent[b]) mask |= 1 << b;
+        D.anc_mask[i] = mask;
+    }
+    for (int j = 0; j < NJ; j++) {
+        D.q_lo[j] = (float)m.q_lo[j]; D.q_hi[j] = (float)m.q_hi[j]; D.tau_max[j] = (float)m.tau_max[j];
+        D.damping[j] = (float)m.joint_damping[j]; D.pd_p[j] = (float)m.pd_p[j]; D.pd_d[j] = (float)m.pd_d[j];
+        D.init_q[j] = (float)m.init_q[j];
+    }
+    for (int c = 0; c < SS_NCOL; c++) {
+        for (int k = 0; k < 3; k++) { D.col_p0[c][k] = (float)m.col_p0[c][k]; D.col_p1[c][k] = (float)m.col_p1[c][k]; }
+        D.col_radius[c] = (float)m.col_radius[c]; D.col_body[c] = m.col_body[c]; D.col_foot[c] = m.col_foot[c];
+    }
+    for (int f = 0; f < 2; f++) { D.foot_body[f] = m.foot_body[f]; for (int k = 0; k < 3; k++) D.foot_ref[f][k] = (float)m.foot_ref[f][k]; }
+    D.contact_breaking = (float)m.contact_breaking; D.gravity = (float)p.gravity; D.dt = (float)p.dt; D.erp_limit = (float)p.erp_limit;
+    double kd = p.dt * p.contact_stiffness + p.contact_damping;
+    D.cfm_contact = (float)(1.0 / kd / p.dt); D.erp_contact = (float)(p.dt * p.contact_stiffness / kd);
+    D.friction = (float)p.friction; D.linear_slop = (float)p.linear_slop; D.warmstart = (float)p.warmstart;
+    D.max_coord_vel = (float)p.max_coord_vel; D.limit_max_impulse = (float)p.limit_max_impulse;
+    for (int k = 0; k < 3; k++) D.stone_half[k] = (float)p.stone_half[k];
+    D.stone_box_off = (float)(p.stone_com_z + p.stone_box_z); D.stone_com_z = (float)p.stone_com_z;
+    D.n_substeps = p.n_substeps; D.n_iters = p.n_iters; D.robot_kind = p.robot_kind; D.terrain_mode = p.terrain_mode;
+    D.n_steps = p.n_steps; D.rendered = p.rendered; D.stop_frames = p.stop_frames; D.max_episode_steps = p.max_episode_steps;
+    D.n_phantoms = p.n_phantoms; D.use_sampler = p.use_sampler; D.actuator_mode = p.actuator_mode;
+    D.done_height = (float)p.done_height; D.electricity_cost = (float)p.electricity_cost;
+    D.stall_torque_cost = (float)p.stall_torque_cost; D.joints_at_limit_cost = (float)p.joints_at_limit_cost;
+    for (int k = 0; k < 3; k++) D.init_pos[k] = m.init_pos[k];
+    D.step_radius = p.step_radius; D.r_max = p.r_max; D.tilt_limit_deg = p.tilt_limit_deg; D.mirror_prob = p.mirror_prob;
+    D.control_dt = p.control_dt;
+    for (int k = 0; k < SS_GRID; k++) {
+        D.samples[0][k] = p.yaw_samples[k]; D.samples[1][k] = p.pitch_samples[k]; D.samples[2][k] = p.r_samples[k];
+        D.samples[3][k] = p.xtilt_samples[k]; D.samples[4][k] = p.ytilt_samples[k];
+    }
+}
+
+static int grid_for(int n) { return (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
+
+static int configure_kernels(size_t smem) {
+    CK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(aba_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+
+extern "C" {
+
+const char* ss_last_error(void) { return g_err.c_str(); }
+
+int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t device, const uint32_t* mt_env,
+              const uint32_t* mt_global, ss_env** out) {
+    if (!model || !params || n <= 0 || !mt_env || !out) return fail(SS_ERR_ARG, "ss_create: bad argument");
+    static const int parent_tab[NB] = SS_PARENT_TABLE;
+    for (int i = 0; i < NB; i++)
+        if (model->parent[i] != parent_tab[i]) return fail(SS_ERR_ARG, "ss_create: model topology differs from the compiled-in humanoid tree");
+    if (params->n_steps < 4 || params->n_steps > SS_MAX_STONES || params->rendered < 2 || params->rendered > params->n_steps)
+        return fail(SS_ERR_ARG, "ss_create: n_steps / rendered out of range");
+    if (params->n_substeps < 1 || params->n_substeps > 4) return fail(SS_ERR_ARG, "ss_create: n_substeps must be 1..4");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(SS_ERR_CUDA, "ss_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(SS_ERR_ARG, "ss_create: device index out of range");
+    CK(cudaSetDevice(device));
+    ss_env* E = new ss_env();
+    E->n = n; E->device = device; E->n_steps = params->n_steps; E->rendered = params->rendered;
+    fill_model(E->hm, *model, *params);
+    E->smem = sizeof(BlockSmem);
+    int rc = configure_kernels(E->smem);
+    if (rc) { delete E; return rc; }
+    DevState& S = E->S;
+    S.n = n; S.n_cells = SS_GRID_CELLS;
+    size_t N = (size_t)n;
+    CK(cudaMalloc(&E->dm, sizeof(DevModel)));
+    CK(cudaMemcpy(E->dm, &E->hm, sizeof(DevModel), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&S.pos, N * 3 * sizeof(double)));
+    CK(cudaMalloc(&S.sv, N * 64 * sizeof(float)));
+    CK(cudaMalloc(&S.warm, N * SS_NWARM * sizeof(float)));
+    CK(cudaMalloc(&S.terrain, N * E->n_steps * 6 * sizeof(double)));
+    CK(cudaMalloc(&S.plank, N * E->rendered * 6 * sizeof(double)));
+    CK(cudaMalloc(&S.scal, N * SS_NSCAL * sizeof(double)));
+    CK(cudaMalloc(&S.ints, N * SS_NINT * sizeof(int)));
+    CK(cudaMalloc(&S.mt, N * 2 * SS_MT_WORDS * sizeof(uint32_t)));
+    CK(cudaMalloc(&E->cdf, (size_t)SS_GRID_CELLS * sizeof(double)));
+    S.cdf = E->cdf;
+    CK(cudaMemset(S.sv, 0, N * 64 * sizeof(float)));
+    CK(cudaMemset(S.warm, 0, N * SS_NWARM * sizeof(float)));
+    CK(cudaMemset(S.terrain, 0, N * E->n_steps * 6 * sizeof(double)));
+    CK(cudaMemset(S.plank, 0, N * E->rendered * 6 * sizeof(double)));
+    CK(cudaMemset(S.scal, 0, N * SS_NSCAL * sizeof(double)));
+    CK(cudaMemset(S.ints, 0, N * SS_NINT * sizeof(int)));
+    {
+        std::vector<uint32_t> mt(N * 2 * SS_MT_WORDS, 0u);
+        for (size_t i = 0; i < N; i++) {
+            memcpy(&mt[i * 2 * SS_MT_WORDS], mt_env + i * SS_MT_WORDS, SS_MT_WORDS * 4);
+            if (mt_global) memcpy(&mt[i * 2 * SS_MT_WORDS + SS_MT_WORDS], mt_global, SS_MT_WORDS * 4);
+            else mt[i * 2 * SS_MT_WORDS + SS_MT_WORDS + 624] = 624;
+        }
+        CK(cudaMemcpy(S.mt, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<double> cdf(SS_GRID_CELLS);
+        for (int i = 0; i < SS_GRID_CELLS; i++) cdf[i] = (double)(i + 1) / SS_GRID_CELLS;
+        CK(cudaMemcpy(E->cdf, cdf.data(), cdf.size() * 8, cudaMemcpyHostToDevice));
+        // initial pose (matches the oracle's sso_create): base at init_pos, identity quat, running-start hinges
+        std::vector<float> sv(N * 64, 0.f); std::vector<double> pos(N * 3);
+        for (size_t i = 0; i < N; i++) {
+            sv[i * 64 + 3] = 1.f;
+            for (int j = 0; j < NJ; j++) sv[i * 64 + 4 + j] = (float)model->init_q[j];
+            for (int k = 0; k < 3; k++) pos[i * 3 + k] = model->init_pos[k];
+        }
+        CK(cudaMemcpy(S.sv, sv.data(), sv.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice));
+    }
+    CK(cudaStreamCreateWithFlags(&E->own, cudaStreamNonBlocking));
+    *out = E;
+    return SS_OK;
+}
+
+void ss_destroy(ss_env* E) {
+    if (!E) return;
+    cudaSetDevice(E->device);
+    cudaDeviceSynchronize();
+    DevState& S = E->S;
+    cudaFree(E->dm); cudaFree(S.pos); cudaFree(S.sv); cudaFree(S.warm); cudaFree(S.terrain); cudaFree(S.plank);
+    cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.dbg);
+    cudaFreeHost(E->h_act); cudaFreeHost(E->h_obs); cudaFreeHost(E->h_rew); cudaFreeHost(E->h_epret);
+    cudaFreeHost(E->h_done); cudaFreeHost(E->h_to); cudaFreeHost(E->h_eplen);
+    cudaFree(E->d_act); cudaFree(E->d_obs); cudaFree(E->d_rew); cudaFree(E->d_epret); cudaFree(E->d_done); cudaFree(E->d_to); cudaFree(E->d_eplen);
+    if (E->own) cudaStreamDestroy(E->own);
+    delete E;
+}
+
+int ss_reset_all(ss_env* E, float* obs_dev, void* stream) {
+    if (!E || !obs_dev) return fail(SS_ERR_ARG, "ss_reset_all: bad argument");
+    CK(cudaSetDevice(E->device));
+    env_reset_kernel<<<grid_for(E->n), BLOCK, E->smem, (cudaStream_t)stream>>>(E->dm, E->S, obs_dev);
+    E->launches++;
+    CK(cudaGetLastError());
+    return SS_OK;
+}
+
+static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el,
+                       cudaStream_t st, int physics) {
+    env_step_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics);
+    E->launches++;
+    CK(cudaGetLastError());
+    return SS_OK;
+}
+
+int ss_step(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, uint8_t* timeout_dev,
+            float* ep_ret_dev, int32_t* ep_len_dev, void* stream) {
+    if (!E || !act_dev || !obs_dev || !rew_dev || !done_dev || !timeout_dev || !ep_ret_dev || !ep_len_dev)
+        return fail(SS_ERR_ARG, "ss_step: null buffer");
+    CK(cudaSetDevice(E->device));
+    return launch_step(E, act_dev, obs_dev, rew_dev, done_dev, timeout_dev, ep_ret_dev, ep_len_dev, (cudaStream_t)stream, 1);
+}
+
+int ss_env_post(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream) {
+    if (!E || !act_dev || !obs_dev || !rew_dev || !done_dev) return fail(SS_ERR_ARG, "ss_env_post: null buffer");
+    CK(cudaSetDevice(E->device));
+    return launch_step(E, act_dev, obs_dev, rew_dev, done_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream, 0);
+}
+
+static int ensure_staging(ss_env* E) {
+    if (E->h_act) return SS_OK;
+    size_t N = (size_t)E->n;
+    CK(cudaMallocHost(&E->h_act, N * NJ * 4)); CK(cudaMallocHost(&E->h_obs, N * SS_OBS * 4));
+    CK(cudaMallocHost(&E->h_rew, N * 4)); CK(cudaMallocHost(&E->h_epret, N * 4));
+    CK(cudaMallocHost(&E->h_done, N)); CK(cudaMallocHost(&E->h_to, N)); CK(cudaMallocHost(&E->h_eplen, N * 4));
+    CK(cudaMalloc(&E->d_act, N * NJ * 4)); CK(cudaMalloc(&E->d_obs, N * SS_OBS * 4));
+    CK(cudaMalloc(&E->d_rew, N * 4)); CK(cudaMalloc(&E->d_epret, N * 4));
+    CK(cudaMalloc(&E->d_done, N)); CK(cudaMalloc(&E->d_to, N)); CK(cudaMalloc(&E->d_eplen, N * 4));
+    return SS_OK;
+}
+
+int ss_step_host(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el) {
+    if (!E || !act || !obs || !rew || !done || !to || !er || !el) return fail(SS_ERR_ARG, "ss_step_host: null buffer");
+    CK(cudaSetDevice(E->device));
+    int rc = ensure_staging(E); if (rc) return rc;
+    size_t N = (size_t)E->n; cudaStream_t st = E->own;
+    memcpy(E->h_act, act, N * NJ * 4);
+    CK(cudaMemcpyAsync(E->d_act, E->h_act, N * NJ * 4, cudaMemcpyHostToDevice, st));
+    rc = launch_step(E, E->d_act, E->d_obs, E->d_rew, E->d_done, E->d_to, E->d_epret, E->d_eplen, st, 1); if (rc) return rc;
+    CK(cudaMemcpyAsync(E->h_obs, E->d_obs, N * SS_OBS * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(E->h_rew, E->d_rew, N * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(E->h_done, E->d_done, N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(E->h_to, E->d_to, N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(E->h_epret, E->d_epret, N * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(E->h_eplen, E->d_eplen, N * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(obs, E->h_obs, N * SS_OBS * 4); memcpy(rew, E->h_rew, N * 4); memcpy(done, E->h_done, N);
+    memcpy(to, E->h_to, N); memcpy(er, E->h_epret, N * 4); memcpy(el, E->h_eplen, N * 4);
+    return SS_OK;
+}
+
+int ss_reset_host(ss_env* E, float* obs) {
+    if (!E || !obs) return fail(SS_ERR_ARG, "ss_reset_host: null buffer");
+    CK(cudaSetDevice(E->device));
+    int rc = ensure_staging(E); if (rc) return rc;
+    rc = ss_reset_all(E, E->d_obs, E->own); if (rc) return rc;
+    CK(cudaMemcpyAsync(E->h_obs, E->d_obs, (size_t)E->n * SS_OBS * 4, cudaMemcpyDeviceToHost, E->own));
+    CK(cudaStreamSynchronize(E->own));
+    memcpy(obs, E->h_obs, (size_t)E->n * SS_OBS * 4);
+    return SS_OK;
+}
+
+int ss_set_sample_cdf(ss_env* E, const double* cdf, int32_t n_cells, int32_t apply_now, void* stream) {
+    if (!E || !cdf || n_cells != SS_GRID_CELLS) return fail(SS_ERR_ARG, "ss_set_sample_cdf: table must have 11^5 cells");
+    CK(cudaSetDevice(E->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(E->cdf, cdf, (size_t)n_cells * 8, cudaMemcpyHostToDevice));
+    if (apply_now) {
+        resample_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S);
+        E->launches++;
+        CK(cudaGetLastError());
+    }
+    return SS_OK;
+}
+
+int ss_get_state(ss_env* E, ss_state_view* v) {
+    if (!E || !v) return fail(SS_ERR_ARG, "ss_get_state: bad argument");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    size_t N = (size_t)E->n; DevState& S = E->S;
+    if (v->q || v->qd) {
+        std::vector<float> sv(N * 64); std::vector<double> pos(N * 3);
+        CK(cudaMemcpy(sv.data(), S.sv, sv.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pos.data(), S.pos, pos.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; i++) {
+            if (v->q) {
+                double* q = v->q + i * SS_NQ;
+                for (int k = 0; k < 3; k++) q[k] = pos[i * 3 + k];
+                for (int k = 0; k < 4 + NJ; k++) q[3 + k] = sv[i * 64 + k];
+            }
+            if (v->qd) for (int k = 0; k < ND; k++) v->qd[i * ND + k] = sv[i * 64 + 32 + k];
+        }
+    }
+    if (v->warm) {
+        std::vector<float> w(N * SS_NWARM);
+        CK(cudaMemcpy(w.data(), S.warm, w.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < w.size(); i++) v->warm[i] = w[i];
+    }
+    if (v->terrain) CK(cudaMemcpy(v->terrain, S.terrain, N * E->n_steps * 48, cudaMemcpyDeviceToHost));
+    if (v->plank) CK(cudaMemcpy(v->plank, S.plank, N * E->rendered * 48, cudaMemcpyDeviceToHost));
+    if (v->scalars) CK(cudaMemcpy(v->scalars, S.scal, N * SS_NSCAL * 8, cudaMemcpyDeviceToHost));
+    if (v->ints) CK(cudaMemcpy(v->ints, S.ints, N * SS_NINT * 4, cudaMemcpyDeviceToHost));
+    if (v->mt) CK(cudaMemcpy(v->mt, S.mt, N * 2 * SS_MT_WORDS * 4, cudaMemcpyDeviceToHost));
+    return SS_OK;
+}
+
+int ss_set_state(ss_env* E, const ss_state_view* v) {
+    if (!E || !v) return fail(SS_ERR_ARG, "ss_set_state: bad argument");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    size_t N = (size_t)E->n; DevState& S = E->S;
+    if (v->q || v->qd) {
+        std::vector<float> sv(N * 64); std::vector<double> pos(N * 3);
+        CK(cudaMemcpy(sv.data(), S.sv, sv.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pos.data(), S.pos, pos.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; i++) {
+            if (v->q) {
+                const double* q = v->q + i * SS_NQ;
+                for (int k = 0; k < 3; k++) pos[i * 3 + k] = q[k];
+                for (int k = 0; k < 4 + NJ; k++) sv[i * 64 + k] = (float)q[3 + k];
+            }
+            if (v->qd) for (int k = 0; k < ND; k++) sv[i * 64 + 32 + k] = (float)v->qd[i * ND + k];
+        }
+        CK(cudaMemcpy(S.sv, sv.data(), sv.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice));
+    }
+    if (v->warm) {
+        std::vector<float> w(N * SS_NWARM);
+        for (size_t i = 0; i < w.size(); i++) w[i] = (float)v->warm[i];
+        CK(cudaMemcpy(S.warm, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (v->terrain) CK(cudaMemcpy(S.terrain, v->terrain, N * E->n_steps * 48, cudaMemcpyHostToDevice));
+    if (v->plank) CK(cudaMemcpy(S.plank, v->plank, N * E->rendered * 48, cudaMemcpyHostToDevice));
+    if (v->scalars) CK(cudaMemcpy(S.scal, v->scalars, N * SS_NSCAL * 8, cudaMemcpyHostToDevice));
+    if (v->ints) CK(cudaMemcpy(S.ints, v->ints, N * SS_NINT * 4, cudaMemcpyHostToDevice));
+    if (v->mt) CK(cudaMemcpy(S.mt, v->mt, N * 2 * SS_MT_WORDS * 4, cudaMemcpyHostToDevice));
+    return SS_OK;
+}
+
+int ss_enable_substep_trace(ss_env* E, int32_t on) {
+    if (!E) return fail(SS_ERR_ARG, "ss_enable_substep_trace: bad argument");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    DevState& S = E->S;
+    if (on && !S.trace_q) {
+        CK(cudaMalloc(&S.trace_q, (size_t)4 * E->n * SS_NQ * 8)); CK(cudaMalloc(&S.trace_qd, (size_t)4 * E->n * ND * 8));
+        CK(cudaMemset(S.trace_q, 0, (size_t)4 * E->n * SS_NQ * 8)); CK(cudaMemset(S.trace_qd, 0, (size_t)4 * E->n * ND * 8));
+    } else if (!on && S.trace_q) {
+        cudaFree(S.trace_q); cudaFree(S.trace_qd); S.trace_q = S.trace_qd = nullptr;
+    }
+    return SS_OK;
+}
+
+int ss_substep_trace(ss_env* E, double* q, double* qd) {
+    if (!E || !q || !qd) return fail(SS_ERR_ARG, "ss_substep_trace: bad argument");
+    if (!E->S.trace_q) return fail(SS_ERR_STATE, "ss_substep_trace: tracing is not enabled");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(q, E->S.trace_q, (size_t)4 * E->n * SS_NQ * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(qd, E->S.trace_qd, (size_t)4 * E->n * ND * 8, cudaMemcpyDeviceToHost));
+    return SS_OK;
+}
+
+/* diagnostics for the parity tests: per-env dump of the LAST substep's H, C, contact candidates, rows, Delassus
+ * matrix (ssb::DBG_* layout).  out_host [N, ss_debug_floats()] */
+int32_t ss_debug_floats(void) { return DBG_FLOATS; }
+int ss_enable_debug(ss_env* E, int32_t on) {
+    if (!E) return fail(SS_ERR_ARG, "ss_enable_debug: bad argument");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    if (on && !E->S.dbg) { CK(cudaMalloc(&E->S.dbg, (size_t)E->n * DBG_FLOATS * 4)); CK(cudaMemset(E->S.dbg, 0, (size_t)E->n * DBG_FLOATS * 4)); }
+    else if (!on && E->S.dbg) { cudaFree(E->S.dbg); E->S.dbg = nullptr; }
+    return SS_OK;
+}
+int ss_debug_read(ss_env* E, float* out_host) {
+    if (!E || !out_host || !E->S.dbg) return fail(SS_ERR_STATE, "ss_debug_read: debug dump is not enabled");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out_host, E->S.dbg, (size_t)E->n * DBG_FLOATS * 4, cudaMemcpyDeviceToHost));
+    return SS_OK;
+}
+
+int ss_aba_substep(ss_env* E, float* q_dev, float* qd_dev, const float* tau_dev, int32_t n, void* stream) {
+    if (!E || !q_dev || !qd_dev || !tau_dev || n <= 0) return fail(SS_ERR_ARG, "ss_aba_substep: bad argument");
+    CK(cudaSetDevice(E->device));
+    aba_substep_kernel<<<grid_for(n), BLOCK, E->smem, (cudaStream_t)stream>>>(E->dm, q_dev, qd_dev, tau_dev, n);
+    E->launches++;
+    CK(cudaGetLastError());
+    return SS_OK;
+}
+
+int ss_gae(const float* rewards, const float* values, const float* masks, const float* bad_masks, float* returns, int32_t T,
+           int32_t N, float gamma, float lam, void* stream) {
+    if (!rewards || !values || !masks || !bad_masks || !returns || T <= 0 || N <= 0) return fail(SS_ERR_ARG, "ss_gae: bad argument");
+    gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, masks, bad_masks, returns, T, N, gamma, lam);
+    CK(cudaGetLastError());
+    return SS_OK;
+}
+
+int32_t ss_num_envs(const ss_env* E) { return E ? E->n : 0; }
+int64_t ss_launch_count(const ss_env* E) { return E ? E->launches : 0; }
+
+}  // extern "C"

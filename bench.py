@@ -96,7 +96,7 @@ def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, seed=8):
     from steppingstone_b200 import model, seeding
     M = model.make_model(wl["kind"])
     P = model.make_params(wl["kind"], None, wl["terrain_mode"])
-    o = Oracle(M, P, n_envs, seeding.env_streams(seed, 0, n_envs), seeding.global_stream(seed), threads=threads)
+    o = Oracle(M, P, n_envs, seeding.env_streams(seed, 0, n_envs), seeding.aux_streams(wl["kind"], seed, 0, n_envs), threads=threads)
     if wl["curriculum"] is not None:
         o.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(wl["curriculum"])))
     o.reset()

@@ -51,18 +51,21 @@ typedef struct ss_state_view {
     double* plank;     /* [N,rendered,6] pose each plank body was last given                      */
     double* scalars;   /* [N,SS_NSCAL]                                                            */
     int32_t* ints;     /* [N,SS_NINT]                                                             */
-    uint32_t* mt;      /* [N,2,SS_MT_WORDS] env np_random stream, then the env's copy of the global numpy stream */
+    uint32_t* mt;      /* [N,2,SS_MT_WORDS] env np_random stream, then the env's aux stream (see ss_create)      */
 } ss_state_view;
 
 typedef struct ss_env ss_env;
 
 /* make_vec_envs(env_id, seed, num_processes, log_dir) -- common/envs_utils.py:48-56, one gym env per
- * worker seeded seed+rank (:25-40).  mt_env_host [n_envs,625] / mt_global_host [625] are the MT19937
- * states of gym's per-env RandomState(seed+rank) and of the forked global numpy stream (q7); the
- * Python host derives them (steppingstone_b200/seeding.py).  first_env is the global index of this
- * shard's env 0 (multi-GPU sharding keeps global numbering). */
+ * worker seeded seed+rank (:25-40).  mt_env_host [n_envs,625] are the MT19937 states of gym's per-env
+ * RandomState(seed+rank) (terrain generator + curriculum sampler draws).  mt_aux_host [n_envs,625] is the
+ * second stream each env owns: for Walker3D the forked copy of the GLOBAL numpy stream its terrain generator
+ * also draws from (walker3d_envs.py:728); for Mike the robot's own RandomState, which the
+ * reference never re-seeds (env_base.py:26,65 vs :131-133) and which decides the left/right mirrored start
+ * (robots.py:846).  The Python host derives both (steppingstone_b200/seeding.py).  Multi-GPU shards pass the
+ * streams of their own global env indices. */
 int ss_create(const ss_model* model, const ss_params* params, int32_t n_envs, int32_t device,
-              const uint32_t* mt_env_host, const uint32_t* mt_global_host, ss_env** out);
+              const uint32_t* mt_env_host, const uint32_t* mt_aux_host, ss_env** out);
 /* VecEnv.close -- envs_utils.py:273-281 */
 void ss_destroy(ss_env* env);
 

@@ -48,7 +48,7 @@ def make_view(state):
 class Oracle:
     """N envs stepped on the CPU by the C restatement."""
 
-    def __init__(self, model, params, n, mt_env, mt_global=None, threads=0):
+    def __init__(self, model, params, n, mt_env, mt_aux=None, threads=0):
         self.lib = ctypes.CDLL(build())
         self.lib.sso_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p]
@@ -58,7 +58,8 @@ class Oracle:
         self.h = ctypes.c_void_p()
         mt_env = np.ascontiguousarray(mt_env, dtype=np.uint32)
         assert mt_env.shape == (n, MTW)
-        g = None if mt_global is None else np.ascontiguousarray(mt_global, dtype=np.uint32)
+        g = None if mt_aux is None else np.ascontiguousarray(mt_aux, dtype=np.uint32)
+        assert g is None or g.shape == (n, MTW)
         rc = self.lib.sso_create(ctypes.byref(model), ctypes.byref(params), n, _ptr(mt_env),
                                  None if g is None else _ptr(g), ctypes.byref(self.h))
         assert rc == 0, rc
@@ -92,6 +93,28 @@ class Oracle:
         assert self.lib.sso_step(self.h, _ptr(act), _ptr(obs), _ptr(rew), _ptr(done), _ptr(timeout),
                                  _ptr(ep_ret), _ptr(ep_len)) == 0
         return obs, rew, done, timeout, ep_ret, ep_len
+
+    def step_injected(self, act, q, qd, contact):
+        """env_step with the physics replaced by the given post-physics state (golden tests)."""
+        act = np.ascontiguousarray(act, dtype=np.float32)
+        q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
+        contact = np.ascontiguousarray(contact, dtype=np.float64)
+        assert q.shape == (self.n, NQ) and qd.shape == (self.n, ND) and contact.shape == (self.n, 2)
+        obs = np.zeros((self.n, OBS), np.float32)
+        rew = np.zeros(self.n, np.float32)
+        done = np.zeros(self.n, np.uint8)
+        timeout = np.zeros(self.n, np.uint8)
+        ep_ret = np.zeros(self.n, np.float32)
+        ep_len = np.zeros(self.n, np.int32)
+        assert self.lib.sso_step_injected(self.h, _ptr(act), _ptr(q), _ptr(qd), _ptr(contact), _ptr(obs), _ptr(rew),
+                                          _ptr(done), _ptr(timeout), _ptr(ep_ret), _ptr(ep_len)) == 0
+        return obs, rew, done, timeout, ep_ret, ep_len
+
+    def feet_fk(self, q):
+        out = np.zeros(6)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert self.lib.sso_feet_fk(self.h, _ptr(q), _ptr(out)) == 0
+        return out.reshape(2, 3)
 
     def env_post(self, act):
         act = np.ascontiguousarray(act, dtype=np.float32)

@@ -57,7 +57,6 @@ static double mt_double(mt_t* s) {
     uint32_t a = mt_u32(s) >> 5, b = mt_u32(s) >> 6;
     return (a * 67108864.0 + b) / 9007199254740992.0;
 }
-static void mt_discard_doubles(mt_t* s, int n) { for (int i = 0; i < 2 * n; i++) (void)mt_u32(s); }
 
 void sso_mt_doubles(uint32_t* mt625, double* out, int32_t n) {
     mt_t s; memcpy(s.mt, mt625, 624 * 4); s.pos = mt625[624];
@@ -769,10 +768,8 @@ static void calc_step_reward(const ss_params* P, env_t* e) {
     e->step_bonus = 0;
     if (e->target_reached && e->reached_count == 1) {
         e->step_bonus = 50 * exp(-fmin(e->foot_dist[0], e->foot_dist[1]) / 0.25);
-        if (P->n_phantoms > 0 && e->next_step % 3 == 0) {            /* phantom.reset draws 1 + 21 values: q11 */
-            mt_discard_doubles(&e->rng, 22);
+        if (P->n_phantoms > 0 && e->next_step % 3 == 0)              /* walker3d_envs.py:1007-1016 (visual only) */
             e->phantom_idx = (e->phantom_idx + 1) % 20;
-        }
     }
     e->target_bonus = 0;
     if (e->next_step == P->n_steps - 1 && e->distance_to_target < 0.15) e->target_bonus = 2.0;
@@ -801,8 +798,13 @@ static void write_obs(const env_t* e, float* obs) {
 static void env_reset(const struct sso_env* S, env_t* e, float* obs) {
     const ss_model* M = &S->M; const ss_params* P = &S->P;
     e->done = 0; e->reached_count = 0;
-    double u = mt_double(&e->rng);                                       /* robots.py:583 / :846 (q10) */
-    e->mirrored = u < P->mirror_prob;
+    /* robots.py:583 / :846: `self.np_random.rand() < p`.  robot.np_random is the RandomState EnvBase.__init__
+     * created with seed(None) (env_base.py:26,65); env.seed(seed+rank) later REPLACES env.np_random
+     * (env_base.py:131-133, envs_utils.py:28) but never re-links the robot's, so this coin (and the phantoms'
+     * draws, walker3d_envs.py:569,861) come from a separate, entropy-seeded stream -- the "aux" stream here.
+     * W3D's test is `< 0` (never true) and unobservable, so no draw is made for it. */
+    e->mirrored = 0;
+    if (P->mirror_prob > 0) { double u = mt_double(&e->grng); e->mirrored = u < P->mirror_prob; }
     memcpy(e->qj, M->init_q, sizeof e->qj);
     if (e->mirrored) {
         static const int R[9] = { 3, 4, 5, 6, 7, 13, 14, 15, 16 }, L[9] = { 8, 9, 10, 11, 12, 17, 18, 19, 20 };
@@ -831,8 +833,7 @@ static void env_reset(const struct sso_env* S, env_t* e, float* obs) {
     delta_to_k_targets(P, e);
     calc_potential(P, e);
     write_obs(e, obs);
-    e->phantom_idx = 0;
-    mt_discard_doubles(&e->rng, 22 * P->n_phantoms);                     /* walker3d_envs.py:859-862 (q11) */
+    e->phantom_idx = 0;          /* walker3d_envs.py:859-862: phantom.reset draws from the robot stream, see above */
     e->elapsed = 0; e->ep_ret = 0; e->ep_len = 0; e->update_terrain = 0; e->started = 1;
 }
 
@@ -851,7 +852,7 @@ static void apply_action(const ss_model* M, const ss_params* P, const env_t* e, 
 static void env_step(const struct sso_env* S, env_t* e, const float* a, float* obs, float* rew, uint8_t* done,
                      uint8_t* timeout, float* ep_ret, int32_t* ep_len, int physics) {
     const ss_model* M = &S->M; const ss_params* P = &S->P;
-    if (physics) {
+    if (physics == 1) {
         double tau[NJ];
         apply_action(M, P, e, a, tau);
         for (int s = 0; s < P->n_substeps; s++) {
@@ -885,7 +886,7 @@ static void env_step(const struct sso_env* S, env_t* e, const float* a, float* o
  * public API
  * ---------------------------------------------------------------------------------------------- */
 int sso_create(const ss_model* model, const ss_params* params, int32_t n, const uint32_t* mt_env,
-               const uint32_t* mt_global, sso_env** out) {
+               const uint32_t* mt_aux, sso_env** out) {
     if (!model || !params || n <= 0 || !mt_env || !out) return SS_ERR_ARG;
     sso_env* S = calloc(1, sizeof *S);
     S->M = *model; S->P = *params; S->n = n;
@@ -898,7 +899,7 @@ int sso_create(const ss_model* model, const ss_params* params, int32_t n, const 
         e->terrain = calloc(6 * params->n_steps, 8);
         e->plank = calloc(6 * params->rendered, 8);
         memcpy(e->rng.mt, mt_env + (size_t)i * SS_MT_WORDS, 624 * 4); e->rng.pos = mt_env[(size_t)i * SS_MT_WORDS + 624];
-        if (mt_global) { memcpy(e->grng.mt, mt_global, 624 * 4); e->grng.pos = mt_global[624]; }
+        if (mt_aux) { memcpy(e->grng.mt, mt_aux + (size_t)i * SS_MT_WORDS, 624 * 4); e->grng.pos = mt_aux[(size_t)i * SS_MT_WORDS + 624]; }
         e->quat[3] = 1;
         memcpy(e->pos, model->init_pos, 24);
         memcpy(e->qj, model->init_q, sizeof e->qj);
@@ -928,6 +929,33 @@ int sso_step(sso_env* S, const float* act, float* obs, float* rew, uint8_t* done
     for (int i = 0; i < S->n; i++)
         env_step(S, &S->e[i], act + 21 * (size_t)i, obs + 60 * (size_t)i, rew + i, done + i, timeout + i, ep_ret + i, ep_len + i, 1);
     (void)nt;
+    return 0;
+}
+
+/* env_step with the physics replaced by an injected post-physics state (golden tests): q [n,28], qd [n,27],
+ * contact [n,2] = per-foot contact flags of the last substep's collision pass */
+int sso_step_injected(sso_env* S, const float* act, const double* q, const double* qd, const double* contact, float* obs,
+                      float* rew, uint8_t* done, uint8_t* timeout, float* ep_ret, int32_t* ep_len) {
+    for (int i = 0; i < S->n; i++) {
+        env_t* e = &S->e[i];
+        memcpy(e->pos, q + (size_t)i * SS_NQ, 24); memcpy(e->quat, q + (size_t)i * SS_NQ + 3, 32); memcpy(e->qj, q + (size_t)i * SS_NQ + 7, NJ * 8);
+        unpack_vel(e, qd + (size_t)i * ND);
+        e->cache_contact[0] = contact[2 * i]; e->cache_contact[1] = contact[2 * i + 1];
+        env_step(S, e, act + 21 * (size_t)i, obs + 60 * (size_t)i, rew + i, done + i, timeout + i, ep_ret + i, ep_len + i, 2);
+    }
+    return 0;
+}
+
+/* feet link COM positions (what getLinkState()[0] reports, bullet_utils.py:94) for a given q [28] */
+int sso_feet_fk(sso_env* S, const double* q, double* out6) {
+    env_t e; memset(&e, 0, sizeof e);
+    memcpy(e.pos, q, 24); memcpy(e.quat, q + 3, 32); memcpy(e.qj, q + 7, NJ * 8);
+    kin_t K; fk(&S->M, &e, &K);
+    for (int i = 0; i < 2; i++) {
+        int b = S->M.foot_body[i]; double t[3];
+        m3v(K.Rw[b], S->M.foot_ref[i], t);
+        for (int k = 0; k < 3; k++) out6[3 * i + k] = K.ow[b][k] + t[k];
+    }
     return 0;
 }
 

@@ -375,8 +375,10 @@ __device__ __forceinline__ void write_obs(const WarpSmem& W, const Env& E, float
 __device__ __forceinline__ void env_reset(const DevModel& M, const DevState& S, WarpSmem& W, int e, Env& E, float* obs, int lane) {
     uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
     E.reached = 0;
-    double u = mt_one_double_warp(mt, E.mtpos, W.u.d, lane);                  // robots.py:583 / :846 (q10)
-    E.mirrored = u < M.mirror_prob;
+    // robots.py:583 / :846: the robot's np_random is NOT the env's seeded stream (oracle env_reset explains): the
+    // mirror coin comes from the per-env aux stream; Walker3D's `< 0` test is unobservable and draws nothing.
+    E.mirrored = 0;
+    if (M.mirror_prob > 0.0) { double u = mt_one_double_warp(mt + SS_MT_WORDS, E.gmtpos, W.u.d, lane); E.mirrored = u < M.mirror_prob; }
     int j = lane - 6, src = j;
     if (E.mirrored) {
         if ((j >= 3 && j <= 7) || (j >= 13 && j <= 16)) src = j + (j <= 7 ? 5 : 4);
@@ -404,8 +406,7 @@ __device__ __forceinline__ void env_reset(const DevModel& M, const DevState& S, 
     delta_to_k_targets(M, S, W, e, E, rpy[2], lane);
     double dist; E.potential = calc_potential(M, E, dist);
     write_obs(W, E, obs, lane);
-    E.phantom_idx = 0;
-    mt_doubles_warp(mt, E.mtpos, nullptr, 22 * M.n_phantoms, lane);           // walker3d_envs.py:859-862 (q11)
+    E.phantom_idx = 0;            // walker3d_envs.py:859-862: the phantoms draw from the robot stream (visual only)
     E.elapsed = 0; E.ep_ret = 0; E.ep_len = 0; E.update_terrain = 0; E.started = 1;
 }
 
@@ -517,10 +518,7 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const DevModel* gm, Dev
     float step_bonus = 0.f;
     if (reached && E.reached == 1) {
         step_bonus = 50.f * expf(-(float)fmin(fd[0], fd[1]) / 0.25f);
-        if (M.n_phantoms > 0 && E.next_step % 3 == 0) {                            // phantom.reset: 22 draws (q11)
-            mt_doubles_warp(S.mt + (size_t)e * 2 * SS_MT_WORDS, E.mtpos, nullptr, 22, lane);
-            E.phantom_idx = (E.phantom_idx + 1) % 20;
-        }
+        if (M.n_phantoms > 0 && E.next_step % 3 == 0) E.phantom_idx = (E.phantom_idx + 1) % 20;   // walker3d_envs.py:1007-1016
     }
     float target_bonus = (E.next_step == M.n_steps - 1 && dist < 0.15) ? 2.f : 0.f;
     delta_to_k_targets(M, S, W, e, E, rpy[2], lane);
@@ -716,7 +714,7 @@ extern "C" {
 const char* ss_last_error(void) { return g_err.c_str(); }
 
 int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t device, const uint32_t* mt_env,
-              const uint32_t* mt_global, ss_env** out) {
+              const uint32_t* mt_aux, ss_env** out) {
     if (!model || !params || n <= 0 || !mt_env || !out) return fail(SS_ERR_ARG, "ss_create: bad argument");
     static const int parent_tab[NB] = SS_PARENT_TABLE;
     for (int i = 0; i < NB; i++)
@@ -759,7 +757,7 @@ int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t
         std::vector<uint32_t> mt(N * 2 * SS_MT_WORDS, 0u);
         for (size_t i = 0; i < N; i++) {
             memcpy(&mt[i * 2 * SS_MT_WORDS], mt_env + i * SS_MT_WORDS, SS_MT_WORDS * 4);
-            if (mt_global) memcpy(&mt[i * 2 * SS_MT_WORDS + SS_MT_WORDS], mt_global, SS_MT_WORDS * 4);
+            if (mt_aux) memcpy(&mt[i * 2 * SS_MT_WORDS + SS_MT_WORDS], mt_aux + i * SS_MT_WORDS, SS_MT_WORDS * 4);
             else mt[i * 2 * SS_MT_WORDS + SS_MT_WORDS + 624] = 624;
         }
         CK(cudaMemcpy(S.mt, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice));

@@ -74,6 +74,28 @@ def global_stream(seed):
     return mt_words(np.random.RandomState(int(seed) % 2 ** 32))
 
 
+ROBOT_STREAM_OFFSET = 0x5EED0000
+
+
+def aux_streams(robot_kind, seed, first_env, n_envs):
+    """[n_envs, 625] second stream of each env (``ss_create`` mt_aux_host).
+
+    Walker3D: every env gets a copy of the global numpy stream (``generate_step_placements`` draws the
+    up/down/flat pitch choice from ``np.random.rand()``, walker3d_envs.py:728; forked workers all inherit the
+    parent's ``np.random.seed(seed)`` state, common/sacred_utils.py:64-71).
+    Mike: the robot's own ``np_random``.  ``EnvBase.__init__`` links it to the RandomState made by
+    ``seed(None)`` (env_base.py:26,65) and ``env.seed(seed+rank)`` replaces only the env's (:131-133), so in
+    the reference this stream is seeded from OS entropy; here it is ``RandomState(seed + rank + 0x5EED0000)``
+    so that runs are reproducible.  It decides the mirrored start pose (robots.py:846)."""
+    out = np.empty((n_envs, MT_WORDS), dtype=np.uint32)
+    if robot_kind == 0:
+        out[:] = global_stream(seed)
+    else:
+        for i in range(n_envs):
+            out[i] = mt_words(np.random.RandomState((int(seed) + first_env + i + ROBOT_STREAM_OFFSET) % 2 ** 32))
+    return out
+
+
 def curriculum_table(level, grid=11, max_curriculum=5):
     """``update_curriculum`` (walker3d_envs.py:1346-1356 / mike.py:856-866): yaw_pitch_r_tilt_prob."""
     c = min(int(level), max_curriculum)

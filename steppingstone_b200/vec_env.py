@@ -73,10 +73,10 @@ class BatchedStepperEnv:
             device = 0
         self.device_index = int(getattr(device, "index", device) or 0)
         mt_env = seeding.env_streams(self.seed, self.first_env, self.num_envs)
-        mt_glob = seeding.global_stream(self.seed)
+        mt_aux = seeding.aux_streams(self.robot_kind, self.seed, self.first_env, self.num_envs)
         self._h = ctypes.c_void_p()
         native.check(self._lib.ss_create(ctypes.byref(self._model), ctypes.byref(self._params), self.num_envs,
-                                         self.device_index, mt_env.ctypes.data, mt_glob.ctypes.data,
+                                         self.device_index, mt_env.ctypes.data, mt_aux.ctypes.data,
                                          ctypes.byref(self._h)), "ss_create")
         self._t0 = time.time()
         self._pending = None

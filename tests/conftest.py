@@ -34,7 +34,7 @@ def make_oracle(kind, n, seed=8, threads=0, params=None, terrain_mode=None):
     from steppingstone_b200 import model, seeding
     M = model.make_model(kind)
     P = model.make_params(kind, params, terrain_mode)
-    return Oracle(M, P, n, seeding.env_streams(seed, 0, n), seeding.global_stream(seed), threads=threads)
+    return Oracle(M, P, n, seeding.env_streams(seed, 0, n), seeding.aux_streams(kind, seed, 0, n), threads=threads)
 
 
 def make_gpu_env(kind, n, seed=8, output="numpy", params=None, terrain_mode=None):

@@ -244,8 +244,8 @@ def run_b200(args, wl):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu, k_cpu = args.ref_envs, 16
-            rate, dt = cpu_port_rate(wl, n_cpu, k_cpu, 2)
+            n_cpu, k_cpu = 2048, 192       # ~10-30 s of CPU work on a 16..32-core host
+            rate, dt = cpu_port_rate(wl, n_cpu, k_cpu, 4)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                    "sample": "%d envs x %d steps of the same workload, %d OpenMP threads, %.1f s" % (n_cpu, k_cpu, cores, dt)}
         line = {
@@ -286,7 +286,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=8192, help="envs per GPU")
     ap.add_argument("--workload", default="w3d-flat", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-envs", type=int, default=256, help="envs per step of the CPU arm's bounded sample")
+    ap.add_argument("--ref-envs", type=int, default=2048, help="envs per step of the CPU arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

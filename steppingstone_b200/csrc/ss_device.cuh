@@ -201,6 +201,24 @@ __device__ __forceinline__ Xf fk_warp(const DevModel& M, const float* quat, floa
     return X;
 }
 
+// LDL^T elimination step K (lane i owns row i of the symmetric matrix); compile-time recursion keeps Hr in registers
+template <int K>
+__device__ __forceinline__ void ldl_steps(float (&Hr)[ND], float& myDinv, int lane) {
+    if constexpr (K < ND) {
+        float dk = shfl(Hr[K], K);
+        float inv = 1.f / dk;
+        if (lane == K) myDinv = inv;
+        float lik = Hr[K] * inv;
+#pragma unroll
+        for (int j = K + 1; j < ND; j++) {
+            float hkj = shfl(Hr[j], K);
+            if (lane > K) Hr[j] -= lik * hkj;
+        }
+        if (lane > K) Hr[K] = lik;
+        ldl_steps<K + 1>(Hr, myDinv, lane);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // dynamics: builds H (joint-space inertia, common frame) and its LDL^T in shared memory, returns the
 // unconstrained generalised acceleration in lane = dof layout.
@@ -367,24 +385,13 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WarpSmem& W, c
     for (int j = 0; j < ND; j++) Hr[j] = lane < ND ? H[lane * HS + j] : (j == lane ? 1.f : 0.f);
     if (dbg) {
         if (lane < ND) {
+#pragma unroll
             for (int j = 0; j < ND; j++) dbg[DBG_H + lane * ND + j] = Hr[j];
             dbg[DBG_C + lane] = Cdof;
         }
     }
     float myDinv = 1.f;
-#pragma unroll
-    for (int k = 0; k < ND; k++) {
-        float dk = shfl(Hr[k], k);
-        float inv = 1.f / dk;
-        if (lane == k) myDinv = inv;
-        float lik = Hr[k] * inv;
-#pragma unroll
-        for (int j = k + 1; j < ND; j++) {
-            float hkj = shfl(Hr[j], k);
-            if (lane > k) Hr[j] -= lik * hkj;
-        }
-        if (lane > k) Hr[k] = lik;
-    }
+    ldl_steps<0>(Hr, myDinv, lane);
     if (lane < ND) {
 #pragma unroll
         for (int j = 0; j < ND; j++) H[lane * HS + j] = Hr[j];
@@ -658,27 +665,34 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
             d[0] = (float)rtype; d[1] = invD; d[2] = rhs; d[3] = rel; d[4] = diag; d[5] = lam;
             for (int s = 0; s < 32; s++) dbg[DBG_ROWS + 4 + 32 * 6 + lane * 32 + s] = (s < nr && lane < nr) ? A[r * AS + s] : 0.f;
         }
-        // ---- projected Gauss-Seidel in constraint space (btMultiBodyConstraintSolver::solveSingleIteration order) ----
-        const int nsrc = nidx >= 0 ? nidx : lane;
+        // ---- projected Gauss-Seidel in constraint space (btMultiBodyConstraintSolver::solveSingleIteration order:
+        //      limit rows in alternating direction, then all normals, then all friction rows).
+        //      Every lane evaluates its own row update each row-step (branch-free); the owner of row rr publishes its
+        //      impulse change with one shuffle and all lanes fold it into their J.dv accumulator.  Friction bounds
+        //      depend on the normal impulse, which only changes in the normal block: one shuffle per iteration.
+        const bool isfric = nidx >= 0;
+        const int nsrc = isfric ? nidx : lane;
         const float mu = M.friction;
+        const float* Arow = A + r * AS;
+        float lo_c = lo, hi_c = hi;
+        bool live = !isfric;
+        auto row_step = [&](int rr) {
+            float d = fmaf(-jdv, invD, fmaf(-lam, cfmt, rhs));
+            float sum = fminf(fmaxf(lam + d, lo_c), hi_c);
+            float mine = live ? sum - lam : 0.f;
+            float dl = shfl(mine, rr);
+            if (lane == rr && live) lam = sum;
+            jdv = fmaf(Arow[rr], dl, jdv);
+        };
         for (int it = 0; it < M.n_iters; it++) {
-            for (int s = 0; s < nr; s++) {
-                int rr = s < nl ? ((it & 1) ? s : nl - 1 - s) : s;
-                float ln = shfl(lam, nsrc);
-                float dl = 0.f;
-                if (lane == rr) {
-                    float lo_ = lo, hi_ = hi; bool skip = false;
-                    if (nidx >= 0) { if (!(ln > 0.f)) skip = true; lo_ = -mu * ln; hi_ = mu * ln; }
-                    if (!skip) {
-                        dl = rhs - lam * cfmt - jdv * invD;
-                        float sum = lam + dl;
-                        if (sum < lo_) { dl = lo_ - lam; sum = lo_; } else if (sum > hi_) { dl = hi_ - lam; sum = hi_; }
-                        lam = sum;
-                    }
-                }
-                dl = shfl(dl, rr);
-                jdv += A[r * AS + rr] * dl;
-            }
+            if (it & 1) { for (int s = 0; s < nl; s++) row_step(s); }
+            else { for (int s = nl - 1; s >= 0; s--) row_step(s); }
+#pragma unroll 4
+            for (int rr = nl; rr < nl + nc; rr++) row_step(rr);
+            float ln = shfl(lam, nsrc);
+            if (isfric) { live = ln > 0.f; hi_c = mu * ln; lo_c = -hi_c; }
+#pragma unroll 4
+            for (int rr = nl + nc; rr < nr; rr++) row_step(rr);
         }
         if (dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
         // ---- velocity update: dv = L^-T sum_r w_r lam_r ----

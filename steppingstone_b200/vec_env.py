@@ -23,6 +23,7 @@ from . import model as _model
 from . import native, seeding
 
 OBS_DIM, ACT_DIM = 60, 21
+_NO_INFO = {}
 
 
 class Box:
@@ -128,8 +129,10 @@ class BatchedStepperEnv:
                                                 self._ep_ret.ctypes.data, self._ep_len.ctypes.data), "ss_step_host")
             dones = self._done.astype(bool)
             t = round(time.time() - self._t0, 6)
-            infos = [{} for _ in range(self.num_envs)]
+            # one shared empty dict for the envs that did not finish (train.py:446-454 only reads keys)
+            infos = [_NO_INFO] * self.num_envs
             for i in np.nonzero(dones)[0]:
+                infos[i] = {}
                 infos[i]["episode"] = {"r": round(float(self._ep_ret[i]), 6), "l": int(self._ep_len[i]), "t": t}
                 if self._timeout[i]:
                     infos[i]["bad_transition"] = True

@@ -10,6 +10,9 @@
 // Reference call sites replaced: pybullet.stepSimulation via World.step (mocca_envs/bullet_utils.py:331-332)
 // and the env logic of mocca_envs/walker3d_envs.py:875-1093 / mocca_envs/mike.py:396-603.
 #pragma once
+#ifndef SS_SYNC
+#define SS_SYNC 1
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -565,6 +568,9 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
 
     float dv = 0.f;          // constraint velocity change (lane = dof)
     float newwarm = 0.f;
+#if SS_SYNC >= 2
+    __syncthreads();         // phase alignment: row build
+#endif
     if (nr > 0) {
         // publish row definitions
         if (lviol && lidx < MAXL) { W.lim[lidx][0] = (float)(lane - 6); W.lim[lidx][1] = lviol == 1 ? 1.f : -1.f; W.lim[lidx][2] = lpen; }
@@ -665,6 +671,9 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
             d[0] = (float)rtype; d[1] = invD; d[2] = rhs; d[3] = rel; d[4] = diag; d[5] = lam;
             for (int s = 0; s < 32; s++) dbg[DBG_ROWS + 4 + 32 * 6 + lane * 32 + s] = (s < nr && lane < nr) ? A[r * AS + s] : 0.f;
         }
+#if SS_SYNC >= 3
+        __syncwarp();
+#endif
         // ---- projected Gauss-Seidel in constraint space (btMultiBodyConstraintSolver::solveSingleIteration order:
         //      limit rows in alternating direction, then all normals, then all friction rows).
         //      Every lane evaluates its own row update each row-step (branch-free); the owner of row rr publishes its
@@ -745,7 +754,9 @@ __device__ __forceinline__ double mt_make_double(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 // draw `count` doubles into out[] (out == nullptr discards them).  pos is warp-uniform.
-__device__ __forceinline__ void mt_doubles_warp(uint32_t* mt, int& pos, double* out, int count, int lane) {
+// (out of line on purpose: it is cold code -- resets and stone advances -- and inlining it at every call site
+// made up a third of the step kernel's instructions, which the hot substep loop then fought for I-cache with)
+__device__ __noinline__ int mt_doubles_impl(uint32_t* mt, int pos, double* out, int count, int lane) {
     int i = 0;
     while (i < count) {
         if (pos >= 624) { mt_twist_warp(mt, lane); pos = 0; }
@@ -765,6 +776,10 @@ __device__ __forceinline__ void mt_doubles_warp(uint32_t* mt, int& pos, double* 
         }
     }
     __syncwarp();
+    return pos;
+}
+__device__ __forceinline__ void mt_doubles_warp(uint32_t* mt, int& pos, double* out, int count, int lane) {
+    pos = mt_doubles_impl(mt, pos, out, count, lane);
 }
 __device__ __forceinline__ double mt_one_double_warp(uint32_t* mt, int& pos, double* scratch, int lane) {
     mt_doubles_warp(mt, pos, scratch, 1, lane);

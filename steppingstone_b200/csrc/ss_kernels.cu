@@ -13,7 +13,16 @@
 
 namespace ssb {
 
-constexpr int WARPS_PER_BLOCK = 4;
+// CTA shape of the env kernels.  The substep loop is ~8k straight-line instructions (128 KB): warps that drift apart
+// thrash the instruction caches (ncu: stall_no_instruction was the top stall).  8 warps per CTA re-aligned by one
+// __syncthreads() per substep share their instruction fetches: 7.2M -> 10.2M env-steps/s at N=8192 (profiles/).
+#ifndef SS_WPB
+#define SS_WPB 8
+#endif
+#ifndef SS_SYNC
+#define SS_SYNC 1
+#endif
+constexpr int WARPS_PER_BLOCK = SS_WPB;
 constexpr int BLOCK = 32 * WARPS_PER_BLOCK;
 
 struct alignas(16) BlockSmem {
@@ -410,6 +419,13 @@ __device__ __forceinline__ void env_reset(const DevModel& M, const DevState& S, 
     E.elapsed = 0; E.ep_ret = 0; E.ep_len = 0; E.update_terrain = 0; E.started = 1;
 }
 
+// Cold path, one out-of-line copy shared by the step and reset kernels: reload the env from memory, reset, store.
+__device__ __noinline__ void env_reset_from_memory(const DevModel* Mp, const DevState* Sp, WarpSmem* Wp, int e, float* obs, int lane) {
+    Env E; env_load(*Sp, e, lane, E);
+    env_reset(*Mp, *Sp, *Wp, e, E, obs, lane);
+    env_store(*Sp, e, lane, E);
+}
+
 // stone boxes of the 4 candidate slots around next_step, relative to the step-start base position
 __device__ __forceinline__ void setup_stones(const DevModel& M, const DevState& S, WarpSmem& W, int e, const Env& E, int lane) {
     if (lane < 4) {
@@ -450,8 +466,15 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const DevModel* gm, Dev
     stage_model(B, gm);
     const DevModel& M = B.M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (e >= S.n) return;
+    const int e_raw = blockIdx.x * WARPS_PER_BLOCK + warp;
+#if SS_SYNC
+    const bool ghost = e_raw >= S.n;            // keeps hitting the block barriers, stores nothing
+    const int e = ghost ? S.n - 1 : e_raw;
+#else
+    if (e_raw >= S.n) return;
+    const bool ghost = false;
+    const int e = e_raw;
+#endif
     WarpSmem& W = B.W[warp];
     Env E; env_load_phys(S, e, lane, E);
 
@@ -473,9 +496,12 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const DevModel* gm, Dev
         setup_stones(M, S, W, e, E, lane);
         float dpos[3] = { 0.f, 0.f, 0.f };
         for (int s = 0; s < M.n_substeps; s++) {
+#if SS_SYNC
+            __syncthreads();                     // re-align the CTA's warps so that they share instruction fetches
+#endif
             float* dbg = (S.dbg && s == M.n_substeps - 1) ? S.dbg + (size_t)e * DBG_FLOATS : nullptr;
             cflags = substep_warp(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg);
-            if (S.trace_q && s < 4) {
+            if (S.trace_q && s < 4 && !ghost) {
                 double* tq = S.trace_q + ((size_t)s * S.n + e) * SS_NQ;
                 double* tv = S.trace_qd + ((size_t)s * S.n + e) * ND;
                 if (lane < 3) tq[lane] = E.pos[lane] + (double)(lane == 0 ? dpos[0] : lane == 1 ? dpos[1] : dpos[2]);
@@ -487,6 +513,7 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const DevModel* gm, Dev
 #pragma unroll
         for (int i = 0; i < 3; i++) E.pos[i] += (double)dpos[i];
     }
+    if (ghost) return;
     env_load_rest(S, e, lane, E);
     if (cflags >= 0) { E.cache_contact[0] = (cflags & 1) ? 1.f : 0.f; E.cache_contact[1] = (cflags & 2) ? 1.f : 0.f; }
 
@@ -543,8 +570,8 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const DevModel* gm, Dev
         timeout[e] = (d && E.elapsed == M.max_episode_steps) ? 1 : 0;
         ep_ret[e] = (float)(rint(E.ep_ret * 1e6) / 1e6); ep_len[e] = E.ep_len;
     }
-    if (d) { __syncwarp(); env_reset(M, S, W, e, E, o, lane); }                     // envs_utils.py:646-649
     env_store(S, e, lane, E);
+    if (d) { __syncwarp(); env_reset_from_memory(&M, &S, &W, e, o, lane); }         // envs_utils.py:646-649
 }
 
 __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const DevModel* gm, DevState S, float* __restrict__ obs) {
@@ -553,9 +580,7 @@ __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const DevModel* gm, De
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (e >= S.n) return;
-    Env E; env_load(S, e, lane, E);
-    env_reset(B.M, S, B.W[warp], e, E, obs + (size_t)e * SS_OBS, lane);
-    env_store(S, e, lane, E);
+    env_reset_from_memory(&B.M, &S, &B.W[warp], e, obs + (size_t)e * SS_OBS, lane);
 }
 
 // update_sample_prob's immediate re-sample (walker3d_envs.py:1317-1320): envs whose update_terrain flag is set

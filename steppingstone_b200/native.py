@@ -96,9 +96,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if needs_build():
-        build_native()
-    lib = ctypes.CDLL(LIB_PATH)
+    override = os.environ.get("SS_B200_LIB")          # experiments only: a differently-tuned build of the same sources
+    if override:
+        lib = ctypes.CDLL(override)
+    else:
+        if needs_build():
+            build_native()
+        lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)           # AttributeError if the symbol is missing: fail loudly
         fn.restype = res

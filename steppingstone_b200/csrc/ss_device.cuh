@@ -25,8 +25,9 @@
 namespace ssb {
 
 constexpr int NB = SS_NB, NJ = SS_NJ, ND = SS_NDOF;
-constexpr int HS = 29;   // row stride of H / L in shared memory (odd -> conflict-free row-per-lane access)
-constexpr int ZS = 29;   // row stride of Z
+constexpr int HS = 28;   // row stride of H / L in shared memory: 16-byte aligned rows; a lane reads ITS row with 7 LDS.128
+                         // (quarter-warp addresses 112 B apart hit disjoint bank groups -> conflict-free)
+constexpr int ZS = 28;   // row stride of Z (same access pattern)
 constexpr int AS = 33;   // row stride of A
 constexpr int MAXC = SS_MAX_CONTACTS, MAXL = SS_MAX_LIMIT_ROWS;
 
@@ -79,8 +80,8 @@ struct alignas(16) WarpSmem {
     float lim[MAXL][4];       // hinge, dir, penetration
     float dinv[32];
     union {
-        struct { float H[ND * HS]; float Z[32 * ZS]; float A[32 * AS]; } s;
-        double d[(ND * HS + 32 * ZS + 32 * AS) / 2];
+        struct { float H[HS * HS]; float Z[32 * ZS]; float A[32 * AS]; } s;
+        double d[(HS * HS + 32 * ZS + 32 * AS) / 2];
     } u;
 };
 
@@ -206,7 +207,7 @@ __device__ __forceinline__ Xf fk_warp(const DevModel& M, const float* quat, floa
 
 // LDL^T elimination step K (lane i owns row i of the symmetric matrix); compile-time recursion keeps Hr in registers
 template <int K>
-__device__ __forceinline__ void ldl_steps(float (&Hr)[ND], float& myDinv, int lane) {
+__device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int lane) {
     if constexpr (K < ND) {
         float dk = shfl(Hr[K], K);
         float inv = 1.f / dk;
@@ -278,7 +279,7 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WarpSmem& W, c
 
     // ---- H (composite rigid body algorithm) ----
     float* H = W.u.s.H;
-    for (int i = lane; i < ND * HS; i += 32) H[i] = 0.f;
+    for (int i = lane; i < HS * HS; i += 32) H[i] = 0.f;
     __syncwarp();
     if (isj) {
         // F = Ic * S : n = Ibar a + h x l ; f = m l - h x a
@@ -383,9 +384,14 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WarpSmem& W, c
     if (lane >= ND) rhs = 0.f;
 
     // ---- LDL^T, lane i owns row i ----
-    float Hr[ND];
+    float Hr[HS];
+    {
+        const float4* row = reinterpret_cast<const float4*>(H + (lane < ND ? lane : ND) * HS);   // row ND is all zero
 #pragma unroll
-    for (int j = 0; j < ND; j++) Hr[j] = lane < ND ? H[lane * HS + j] : (j == lane ? 1.f : 0.f);
+        for (int j = 0; j < HS / 4; j++) { float4 v = row[j]; Hr[4 * j] = v.x; Hr[4 * j + 1] = v.y; Hr[4 * j + 2] = v.z; Hr[4 * j + 3] = v.w; }
+#pragma unroll
+        for (int j = 0; j < ND; j++) if (lane >= ND && j == lane) Hr[j] = 1.f;
+    }
     if (dbg) {
         if (lane < ND) {
 #pragma unroll
@@ -396,8 +402,9 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WarpSmem& W, c
     float myDinv = 1.f;
     ldl_steps<0>(Hr, myDinv, lane);
     if (lane < ND) {
+        float4* row = reinterpret_cast<float4*>(H + lane * HS);
 #pragma unroll
-        for (int j = 0; j < ND; j++) H[lane * HS + j] = Hr[j];
+        for (int j = 0; j < HS / 4; j++) row[j] = make_float4(Hr[4 * j], Hr[4 * j + 1], Hr[4 * j + 2], Hr[4 * j + 3]);
     }
     W.dinv[lane] = myDinv;
     __syncwarp();
@@ -584,9 +591,9 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
 
         // ---- lane = row: Jacobian row, z = L^-1 J^T ----
         const int r = lane;
-        float z[ND];
+        float z[HS];
 #pragma unroll
-        for (int k = 0; k < ND; k++) z[k] = 0.f;
+        for (int k = 0; k < HS; k++) z[k] = 0.f;
         int rtype = -1;      // 0 limit, 1 normal, 2/3 friction
         int nidx = -1; float pen = 0.f, lam = 0.f;
         if (r < nl) {
@@ -618,30 +625,33 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         float rel = 0.f;
 #pragma unroll
         for (int k = 0; k < ND; k++) rel += z[k] * W.vec[k];
-        // forward substitution with the unit lower factor (broadcast reads of L)
+        // forward substitution with the unit lower factor, row by row (broadcast LDS.128 reads of L)
         const float* L = W.u.s.H;
 #pragma unroll
-        for (int k = 0; k < ND - 1; k++) {
-            float zk = z[k];
+        for (int i = 1; i < ND; i++) {
+            const float4* Li = reinterpret_cast<const float4*>(L + i * HS);
+            float acc = z[i];
 #pragma unroll
-            for (int i = k + 1; i < ND; i++) z[i] -= L[i * HS + k] * zk;
+            for (int j = 0; j < (i + 3) / 4; j++) {
+                float4 l = Li[j];
+                if (4 * j < i) acc = fmaf(-l.x, z[4 * j], acc);
+                if (4 * j + 1 < i) acc = fmaf(-l.y, z[4 * j + 1], acc);
+                if (4 * j + 2 < i) acc = fmaf(-l.z, z[4 * j + 2], acc);
+                if (4 * j + 3 < i) acc = fmaf(-l.w, z[4 * j + 3], acc);
+            }
+            z[i] = acc;
         }
         float* Z = W.u.s.Z;
+        {
+            float4* Zr = reinterpret_cast<float4*>(Z + r * ZS);
 #pragma unroll
-        for (int k = 0; k < ND; k++) Z[r * ZS + k] = z[k];
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < ND; k++) z[k] *= W.dinv[k];       // w = D^-1 z
-        // Delassus row: A[r][s] = w_r . z_s
-        float* A = W.u.s.A;
-        float diag = 0.f;
-        for (int s = 0; s < nr; s++) {
-            float a = 0.f;
-#pragma unroll
-            for (int k = 0; k < ND; k++) a += z[k] * Z[s * ZS + k];
-            A[r * AS + s] = a;
-            if (s == r) diag = a;
+            for (int j = 0; j < ZS / 4; j++) Zr[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
         }
+        __syncwarp();
+        // w = D^-1 z ; diagonal of the Delassus matrix first, so that the row can be stored pre-scaled
+        float diag = 0.f;
+#pragma unroll
+        for (int k = 0; k < ND; k++) { float w = z[k] * W.dinv[k]; diag = fmaf(w, z[k], diag); z[k] = w; }
         // row constants (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint / btMultiBodyJointLimitConstraint)
         float invD = 0.f, rhs = 0.f, cfmt = 0.f, lo = 0.f, hi = 0.f;
         if (rtype == 0) {
@@ -658,13 +668,29 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 hi = 1e10f;
             } else rhs = -rel * invD;
         }
+        // Delassus row, scaled by this row's 1/(D + cfm):  At[r][s] = (w_r . z_s) * invD_r
+        float* A = W.u.s.A;
+        for (int s = 0; s < nr; s++) {
+            const float4* Zs = reinterpret_cast<const float4*>(Z + s * ZS);
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < ZS / 4; j++) {
+                float4 v = Zs[j];
+                a = fmaf(z[4 * j], v.x, a); a = fmaf(z[4 * j + 1], v.y, a); a = fmaf(z[4 * j + 2], v.z, a);
+                if (4 * j + 3 < ND) a = fmaf(z[4 * j + 3], v.w, a);
+            }
+            A[r * AS + s] = a * invD;
+        }
         __syncwarp();
         // overwrite Z with w for the final velocity update
+        {
+            float4* Zr = reinterpret_cast<float4*>(Z + r * ZS);
 #pragma unroll
-        for (int k = 0; k < ND; k++) Z[r * ZS + k] = z[k];
-        // warm start: acc_r = sum_s A[r][s] lam_s
-        float jdv = 0.f;
-        for (int s = nl; s < nl + nc; s++) { float ls = shfl(lam, s); jdv += A[r * AS + s] * ls; }
+            for (int j = 0; j < ZS / 4; j++) Zr[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+        }
+        // g_r = rhs_r - (J_r dv) invD_r, maintained incrementally; warm start: dv = sum_s W_s lam_s
+        float g = rhs;
+        for (int s = nl; s < nl + nc; s++) { float ls = shfl(lam, s); g = fmaf(-A[r * AS + s], ls, g); }
         if (dbg) {
             dbg[DBG_ROWS + 0] = (float)nl; dbg[DBG_ROWS + 1] = (float)nc;
             float* d = dbg + DBG_ROWS + 4 + lane * 6;
@@ -682,16 +708,15 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         const bool isfric = nidx >= 0;
         const int nsrc = isfric ? nidx : lane;
         const float mu = M.friction;
+        const float omc = 1.f - cfmt;
         const float* Arow = A + r * AS;
-        float lo_c = lo, hi_c = hi;
-        bool live = !isfric;
+        // friction rows start dead (bounds pinned to the current impulse => no change) until their normal pushes
+        float lo_c = isfric ? lam : lo, hi_c = isfric ? lam : hi;
         auto row_step = [&](int rr) {
-            float d = fmaf(-jdv, invD, fmaf(-lam, cfmt, rhs));
-            float sum = fminf(fmaxf(lam + d, lo_c), hi_c);
-            float mine = live ? sum - lam : 0.f;
-            float dl = shfl(mine, rr);
-            if (lane == rr && live) lam = sum;
-            jdv = fmaf(Arow[rr], dl, jdv);
+            float sum = fminf(fmaxf(fmaf(lam, omc, g), lo_c), hi_c);     // lam + (rhs - lam cfm - J dv invD), clamped
+            float dl = shfl(sum - lam, rr);
+            if (lane == rr) lam = sum;
+            g = fmaf(-Arow[rr], dl, g);
         };
         for (int it = 0; it < M.n_iters; it++) {
             if (it & 1) { for (int s = 0; s < nl; s++) row_step(s); }
@@ -699,7 +724,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
 #pragma unroll 4
             for (int rr = nl; rr < nl + nc; rr++) row_step(rr);
             float ln = shfl(lam, nsrc);
-            if (isfric) { live = ln > 0.f; hi_c = mu * ln; lo_c = -hi_c; }
+            if (isfric) { bool live = ln > 0.f; hi_c = live ? mu * ln : lam; lo_c = live ? -hi_c : lam; }
 #pragma unroll 4
             for (int rr = nl + nc; rr < nr; rr++) row_step(rr);
         }

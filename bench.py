@@ -244,7 +244,7 @@ def run_b200(args, wl):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu, k_cpu = 2048, 192       # ~10-30 s of CPU work on a 16..32-core host
+            n_cpu, k_cpu = 4096, 384       # ~10-30 s of CPU work on a 16..32-core host
             rate, dt = cpu_port_rate(wl, n_cpu, k_cpu, 4)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                    "sample": "%d envs x %d steps of the same workload, %d OpenMP threads, %.1f s" % (n_cpu, k_cpu, cores, dt)}

@@ -91,7 +91,9 @@ class ClockSampler:
 
 
 def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, seed=8):
-    """env-steps/s of the CPU oracle (C port of the reference algorithm) on the host cores."""
+    """env-steps/s of the CPU oracle (C port of the reference algorithm) on the host cores.  The thread count is
+    passed explicitly (OpenMP num_threads clause): torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    threads = threads or (os.cpu_count() or 1)
     from oracle.binding import Oracle
     from steppingstone_b200 import model, seeding
     M = model.make_model(wl["kind"])

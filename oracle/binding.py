@@ -158,6 +158,12 @@ class Oracle:
         assert self.lib.sso_mass_matrix(self.h, i, _ptr(H), _ptr(C)) == 0
         return H, C
 
+    def invariants(self, q, qd):
+        out = np.zeros(12)
+        q = np.ascontiguousarray(q, dtype=np.float64); qd = np.ascontiguousarray(qd, dtype=np.float64)
+        assert self.lib.sso_invariants(self.h, _ptr(q), _ptr(qd), _ptr(out)) == 0
+        return dict(mass=out[0], com=out[1:4].copy(), P=out[4:7].copy(), L=out[7:10].copy(), ke=out[10], pe=out[11])
+
     def contacts(self, i=0):
         out = np.zeros((NWARM, 8))
         assert self.lib.sso_contacts(self.h, i, _ptr(out)) == 0

@@ -1099,6 +1099,52 @@ int sso_mass_matrix(sso_env* S, int32_t i, double* H, double* C) {
     return 0;
 }
 
+/* mechanical invariants of a state (physics sanity tests): out[0] total mass, [1..3] centre of mass, [4..6] linear
+ * momentum, [7..9] angular momentum about the centre of mass, [10] kinetic energy, [11] potential energy (m g z).
+ * Computed body by body from world-frame rigid-body velocities -- independent of the ABA / joint-space code. */
+int sso_invariants(sso_env* S, const double* q, const double* qd, double* out) {
+    const ss_model* M = &S->M;
+    env_t e; memset(&e, 0, sizeof e);
+    memcpy(e.pos, q, 24); memcpy(e.quat, q + 3, 32); memcpy(e.qj, q + 7, NJ * 8);
+    unpack_vel(&e, qd);
+    kin_t K; fk(M, &e, &K);
+    double w[NB][3], vo[NB][3];                 /* world angular velocity and velocity of each frame origin */
+    memcpy(w[0], e.w, 24); memcpy(vo[0], e.v, 24);
+    for (int i = 1; i < NB; i++) {
+        int p = M->parent[i];
+        double r[3] = { K.ow[i][0] - K.ow[p][0], K.ow[i][1] - K.ow[p][1], K.ow[i][2] - K.ow[p][2] }, t[3];
+        cross(w[p], r, t);
+        for (int k = 0; k < 3; k++) { vo[i][k] = vo[p][k] + t[k]; w[i][k] = w[p][k] + K.aw[i][k] * e.qdj[i - 1]; }
+    }
+    double mt = 0, c[3] = { 0, 0, 0 }, P[3] = { 0, 0, 0 }, ke = 0, pe = 0;
+    double cw[NB][3], vc[NB][3], Lb[NB][3];
+    for (int i = 0; i < NB; i++) {
+        double t[3], u[3];
+        m3v(K.Rw[i], M->com[i], t);
+        for (int k = 0; k < 3; k++) cw[i][k] = K.ow[i][k] + t[k];
+        cross(w[i], t, u);
+        for (int k = 0; k < 3; k++) vc[i][k] = vo[i][k] + u[k];
+        double wb[3], Iw[3]; m3tv(K.Rw[i], w[i], wb);
+        const double* in = M->inertia[i];
+        double Ib[3] = { in[0] * wb[0] + in[3] * wb[1] + in[4] * wb[2], in[3] * wb[0] + in[1] * wb[1] + in[5] * wb[2],
+                         in[4] * wb[0] + in[5] * wb[1] + in[2] * wb[2] };
+        m3v(K.Rw[i], Ib, Iw); memcpy(Lb[i], Iw, 24);
+        double m = M->mass[i];
+        mt += m; for (int k = 0; k < 3; k++) { c[k] += m * cw[i][k]; P[k] += m * vc[i][k]; }
+        ke += 0.5 * m * dot3(vc[i], vc[i]) + 0.5 * dot3(w[i], Iw);
+        pe += m * S->P.gravity * cw[i][2];
+    }
+    for (int k = 0; k < 3; k++) c[k] /= mt;
+    double L[3] = { 0, 0, 0 };
+    for (int i = 0; i < NB; i++) {
+        double r[3] = { cw[i][0] - c[0], cw[i][1] - c[1], cw[i][2] - c[2] }, mv[3] = { M->mass[i] * vc[i][0], M->mass[i] * vc[i][1], M->mass[i] * vc[i][2] }, t[3];
+        cross(r, mv, t);
+        for (int k = 0; k < 3; k++) L[k] += t[k] + Lb[i][k];
+    }
+    out[0] = mt; memcpy(out + 1, c, 24); memcpy(out + 4, P, 24); memcpy(out + 7, L, 24); out[10] = ke; out[11] = pe;
+    return 0;
+}
+
 int sso_contacts(sso_env* S, int32_t i, double* out) {
     kin_t K; cand_t cand[SS_NWARM];
     fk(&S->M, &S->e[i], &K);

@@ -85,6 +85,14 @@ struct alignas(16) WarpSmem {
     } u;
 };
 
+// scratch of the dynamics-only kernel (aba_substep): same member names, no constraint-solver storage
+struct alignas(16) WarpSmemDyn {
+    float S[NB][6];
+    float foot[2][12];
+    float dinv[32];
+    struct { struct { float H[HS * HS]; } s; } u;
+};
+
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
@@ -231,7 +239,8 @@ __device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int la
 //   out: acc (lane = dof);  W.u.s.H holds L (unit lower, row stride HS), W.dinv holds 1/D
 //        W.S holds the hinge motion vectors, W.foot the foot body poses
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float dynamics_warp(const DevModel& M, WarpSmem& W, const float* quat, float q_dof, float v_dof,
+template <typename WS>
+__device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const float* quat, float q_dof, float v_dof,
                                                float tau_dof, int lane, float* dbg) {
     const int ss = seg_start(lane), se = seg_end(lane);
     const bool isb = lane < NB, isj = lane >= 1 && lane < NB;

@@ -32,10 +32,18 @@ struct alignas(16) BlockSmem {
     WarpSmem W[WARPS_PER_BLOCK];
 };
 
+struct alignas(16) BlockSmemDyn {
+    DevModel M;
+    unsigned long long bar;
+    unsigned long long pad;
+    WarpSmemDyn W[WARPS_PER_BLOCK];
+};
+
 // ---------------------------------------------------------------------------------------------
 // TMA bulk copy of the constant tables into shared memory (cp.async.bulk -> UBLKCP) + mbarrier wait
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_model(BlockSmem& B, const DevModel* gm) {
+template <typename BS>
+__device__ __forceinline__ void stage_model(BS& B, const DevModel* gm) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&B.bar);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&B.M);
     if (threadIdx.x == 0) {
@@ -599,15 +607,15 @@ __global__ void __launch_bounds__(BLOCK) resample_kernel(const DevModel* gm, Dev
 }
 
 // stand-alone forward-dynamics substep: q [N,28], qd [N,27], tau [N,21] f32 -> q, qd in place (524 B / env-substep)
-__global__ void __launch_bounds__(BLOCK) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
-                                                            const float* __restrict__ tau, int n) {
-    BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
+__global__ void __launch_bounds__(BLOCK, 3) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
+                                                               const float* __restrict__ tau, int n) {
+    BlockSmemDyn& B = *reinterpret_cast<BlockSmemDyn*>(smem_raw);
     stage_model(B, gm);
     const DevModel& M = B.M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (e >= n) return;
-    WarpSmem& W = B.W[warp];
+    WarpSmemDyn& W = B.W[warp];
     float* qe = q + (size_t)e * SS_NQ; float* ve = qd + (size_t)e * ND;
     float a = lane < SS_NQ ? qe[lane] : 0.f;
     float quat[4], pos[3];
@@ -730,7 +738,7 @@ static int configure_kernels(size_t smem) {
     CK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(aba_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(aba_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmemDyn)));
     return 0;
 }
 
@@ -1016,7 +1024,7 @@ int ss_debug_read(ss_env* E, float* out_host) {
 int ss_aba_substep(ss_env* E, float* q_dev, float* qd_dev, const float* tau_dev, int32_t n, void* stream) {
     if (!E || !q_dev || !qd_dev || !tau_dev || n <= 0) return fail(SS_ERR_ARG, "ss_aba_substep: bad argument");
     CK(cudaSetDevice(E->device));
-    aba_substep_kernel<<<grid_for(n), BLOCK, E->smem, (cudaStream_t)stream>>>(E->dm, q_dev, qd_dev, tau_dev, n);
+    aba_substep_kernel<<<grid_for(n), BLOCK, sizeof(BlockSmemDyn), (cudaStream_t)stream>>>(E->dm, q_dev, qd_dev, tau_dev, n);
     E->launches++;
     CK(cudaGetLastError());
     return SS_OK;

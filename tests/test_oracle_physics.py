@@ -1,0 +1,83 @@
+"""CPU: mechanical invariants of the oracle's rigid-body dynamics.
+
+PyBullet itself is unavailable, so the dynamics cannot be compared with the reference's
+numbers; they can be compared with PHYSICS.  `sso_invariants` computes mass, centre of mass, momenta and energy
+body by body from world-frame rigid-body velocities (no ABA / joint-space code involved); the articulated-body
+forward dynamics must then obey, in torque-free flight: d(linear momentum)/dt = M g, conservation of angular
+momentum about the centre of mass, and conservation of total energy (up to the O(h) drift of the semi-implicit
+integrator at h = 1/240 s).  The GPU kernels are tied to the same dynamics by tests/test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_oracle
+
+
+def _random_state(rng, lo, hi, speed):
+    q = np.zeros(28); qd = rng.randn(27) * speed
+    q[:3] = rng.randn(3); q[2] += 5
+    quat = rng.randn(4); q[3:7] = quat / np.linalg.norm(quat)
+    q[7:] = lo + (hi - lo) * rng.uniform(0.3, 0.7, 21)
+    return q, qd
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_total_mass_matches_mjcf_density_rule(kind):
+    o = make_oracle(kind, 1)
+    q, qd = _random_state(np.random.RandomState(0), np.array(o.model.q_lo), np.array(o.model.q_hi), 1.0)
+    inv = o.invariants(q, qd)
+    # walker3d.xml at density 1000: 60.00 kg; mike.xml with the waist forced to 8 kg: 33.8 kg
+    assert abs(inv["mass"] - (60.0 if kind == 0 else 33.77)) < 0.01
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_free_flight_momentum_and_energy(kind):
+    o = make_oracle(kind, 1)
+    lo, hi = np.array(o.model.q_lo), np.array(o.model.q_hi)
+    if kind == 1:
+        lo, hi = lo.copy(), hi.copy(); lo[:3] = -0.3; hi[:3] = 0.3        # the locked abdomen is irrelevant without limits
+    g, h = 9.81, 1.0 / 240.0
+    for trial in range(4):
+        rng = np.random.RandomState(10 + trial)
+        q, qd = _random_state(rng, lo, hi, 0.8)
+        tau = np.zeros((1, 21))
+        i0 = o.invariants(q, qd)
+        n = 60                                                              # 0.25 s of flight
+        for _ in range(n):
+            qn, qdn = o.aba_substep(q[None], qd[None], tau)
+            q, qd = qn[0], qdn[0]
+        i1 = o.invariants(q, qd)
+        M = i0["mass"]
+        dP = i1["P"] - i0["P"]
+        assert np.allclose(dP, [0, 0, -M * g * n * h], atol=4e-3 * M), "linear momentum: dP/dt != M g"
+        Lscale = max(1.0, np.linalg.norm(i0["L"]))
+        assert np.linalg.norm(i1["L"] - i0["L"]) < 2e-2 * Lscale, "angular momentum about the COM is not conserved"
+        # semi-implicit Euler lets the COM lag the parabola by g h t / 2, i.e. the energy reads low by M g (g h t / 2);
+        # apart from that known integrator offset the total energy must be conserved (here to 0.5% of the kinetic energy)
+        E0, E1 = i0["ke"] + i0["pe"], i1["ke"] + i1["pe"]
+        t = n * h
+        offset = -M * g * (g * h * t / 2)
+        assert abs(E1 - E0 - offset) < 0.1 + 5e-3 * i1["ke"], "total energy drifts: %g -> %g (expected offset %g)" % (E0, E1, offset)
+        # centre of mass follows the ballistic parabola (semi-implicit Euler: exact up to h * g * t / 2)
+        t = n * h
+        com_pred = i0["com"] + i0["P"] / M * t + 0.5 * np.array([0, 0, -g]) * t * t
+        assert np.allclose(i1["com"], com_pred, atol=g * h * t)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_internal_torques_do_not_change_momentum(kind):
+    """Hinge torques are internal forces: they must not change linear momentum or angular momentum about the COM."""
+    o = make_oracle(kind, 1)
+    lo, hi = np.array(o.model.q_lo), np.array(o.model.q_hi)
+    if kind == 1:
+        lo, hi = lo.copy(), hi.copy(); lo[:3] = -0.3; hi[:3] = 0.3
+    rng = np.random.RandomState(3)
+    q, qd = _random_state(rng, lo, hi, 0.5)
+    h, g = 1.0 / 240.0, 9.81
+    tau = rng.randn(1, 21) * 30
+    _, qd_free = o.aba_substep(q[None], qd[None], np.zeros((1, 21)))
+    _, qd_torq = o.aba_substep(q[None], qd[None], tau)
+    a = o.invariants(q, qd_free[0]); b = o.invariants(q, qd_torq[0])      # same configuration, the two updated velocities
+    assert np.abs(qd_torq - qd_free).max() > 0.1                            # the torques did act
+    assert np.allclose(a["P"], b["P"], atol=1e-9 * a["mass"])
+    assert np.allclose(a["L"], b["L"], atol=1e-9 * max(1.0, np.linalg.norm(a["L"])))

@@ -820,6 +820,7 @@ static void env_reset(const struct sso_env* S, env_t* e, float* obs) {
      * w = v = 0 after every reset. */
     e->v[0] = e->v[1] = e->v[2] = 0;
     e->w[0] = e->w[1] = e->w[2] = 0;
+    for (int l = 0; l < SS_NWARM; l++) if (!isfinite(e->warm[l])) e->warm[l] = 0;   /* the cache survives resets (q4); a NaN must not */
     /* WalkerBase.reset robots.py:433-439 */
     e->feet_contact[0] = e->feet_contact[1] = 0;
     memset(e->feet_xyz, 0, sizeof e->feet_xyz);

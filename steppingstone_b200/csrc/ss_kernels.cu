@@ -404,6 +404,7 @@ __device__ __forceinline__ void env_reset(const DevModel& M, const DevState& S, 
     float q = 0.f;
     if (j >= 0 && j < NJ) { q = M.init_q[src]; if (E.mirrored && (j == 0 || j == 2)) q = -q; }
     E.q_dof = q; E.v_dof = 0.f;           // resetBasePositionAndOrientation zeroes both base velocities (oracle env_reset)
+    if (!isfinite(E.warm)) E.warm = 0.f;  // the warm-start cache survives resets (q4); a NaN must not
 #pragma unroll
     for (int i = 0; i < 3; i++) E.pos[i] = M.init_pos[i];
     E.quat[0] = E.quat[1] = E.quat[2] = 0.f; E.quat[3] = 1.f;

@@ -326,3 +326,26 @@ def test_roundtrip_properties_full_size():
         assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     st = g.get_state()
     assert np.allclose(np.linalg.norm(st["q"][:, 3:7], axis=1), 1.0, atol=1e-5)
+
+
+def test_soak_large_actions_stay_finite():
+    """2000 control steps of 4096 envs under violent actions (sd 1.0, clipped by apply_action): outputs stay finite,
+    episodes keep ending and restarting, a NaN injected into one env's state is flushed by its next reset."""
+    import torch
+    n = 4096
+    g = make_gpu_env(0, n, output="torch")
+    g.reset()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+    acts = torch.randn(32, n, 21, device="cuda", generator=gen)
+    episodes = 0
+    for t in range(2000):
+        obs, rew, done, info = g.step(acts[t % 32])
+        if t % 100 == 99:
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all(), "non-finite output at step %d" % t
+            episodes += int(done.sum())
+        if t == 500:
+            st = g.get_state(); st["qd"][7, 10] = np.nan; st["warm"][7, 3] = np.nan; g.set_state(st)
+    assert episodes > 0
+    st = g.get_state()
+    assert np.isfinite(st["q"]).all() and np.isfinite(st["qd"]).all() and np.isfinite(st["warm"]).all()
+    assert np.allclose(np.linalg.norm(st["q"][:, 3:7], axis=1), 1.0, atol=1e-4)

@@ -95,6 +95,24 @@ int ss_reset_host(ss_env* env, float* obs_host);
  * stone for envs whose update_terrain flag is set. */
 int ss_set_sample_cdf(ss_env* env, const double* cdf_host, int32_t n_cells, int32_t apply_now, void* stream);
 
+/* set_env_params / set_robot_params -- env_base.py:73-85 through envs_utils.py:560-566: the reference setattr()s
+ * fields of every worker's env / robot (and recomputes the torque limits, robots.py:385-388).  Here the host
+ * rebuilds the two constant tables and this call swaps them in (synchronises `stream`; takes effect from the next
+ * step / reset).  n_steps and rendered cannot change (they size the per-env terrain arrays). */
+int ss_update_tables(ss_env* env, const ss_model* model, const ss_params* params, void* stream);
+
+/* create_temp_states / create_temp_states_1 / create_temp_states_2 -- walker3d_envs.py:1189-1243, mike.py:699-753 through
+ * envs_utils.py:573-578 (value-guided sampling probes read by train.py:247-271).  variant 1: yaw x pitch at r = 0.7
+ * (121 cells); 2: yaw x pitch x r (1331); 5: yaw x pitch x r x x_tilt x y_tilt (161051).  grid_host [5][11] = the
+ * env's fake_{yaw,pitch,r,x_tilt,y_tilt}_samples.  For every env whose update_terrain flag is set, row g of
+ * out_dev [N, cells, 60] f32 is get_temp_state() with the next-next stone moved to grid cell g; other envs get zeros
+ * (self.temp_states).  Reference side effects kept: walk_target stays at the last cell's stone; the stone is then
+ * re-placed from restore_host = (pitch, yaw, dr, x_tilt, y_tilt) (the env's next_next_*; NULL = leave the row as the
+ * sampler wrote it, which is what Mike's restore amounts to).  Stream-ordered, no synchronisation. */
+int64_t ss_temp_state_cells(int32_t variant);
+int ss_create_temp_states(ss_env* env, int32_t variant, const double* grid_host, const double* restore_host,
+                          float* out_dev, void* stream);
+
 /* State access (synchronous). */
 int ss_get_state(ss_env* env, ss_state_view* view);
 int ss_set_state(ss_env* env, const ss_state_view* view);

@@ -128,6 +128,17 @@ class Oracle:
         cdf = np.ascontiguousarray(cdf, dtype=np.float64)
         assert self.lib.sso_set_sample_cdf(self.h, _ptr(cdf), cdf.size, int(apply_now)) == 0
 
+    def create_temp_states(self, variant, grid, restore=None):
+        """create_temp_states_1 / _2 / create_temp_states (variant 1 / 2 / 5) -> [n, G, 60] float32."""
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        assert grid.shape == (5, 11)
+        G = {1: 121, 2: 1331, 5: 161051}[variant]
+        out = np.zeros((self.n, G, OBS), np.float32)
+        r = None if restore is None else np.ascontiguousarray(restore, dtype=np.float64)
+        self.lib.sso_create_temp_states.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        assert self.lib.sso_create_temp_states(self.h, variant, _ptr(grid), None if r is None else _ptr(r), _ptr(out)) == 0
+        return out
+
     def get_state(self):
         st = alloc_state(self.n, self.n_steps, self.rendered)
         v = make_view(st)

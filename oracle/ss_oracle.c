@@ -967,6 +967,44 @@ int sso_env_post(sso_env* S, const float* act, float* obs, float* rew, uint8_t* 
     return 0;
 }
 
+/* create_temp_states walker3d_envs.py:1189-1243 / mike.py:699-753 (variant 1: yaw x pitch at r = 0.7; 2: yaw x pitch x r;
+ * 5: yaw x pitch x r x x_tilt x y_tilt).  For every env whose update_terrain flag is set: the next-next stone is moved
+ * to every grid cell in turn (set_next_next_step_location(pi/2 - pitch, yaw, r, x_tilt, y_tilt)) and get_temp_state()
+ * = concat(get_state(), delta_to_k_targets(2)) is recorded; afterwards the stone is put back with the env's
+ * next_next_* parameters (`restore` = pitch, yaw, dr, x_tilt, y_tilt; NULL = the row the sampler wrote, i.e. unchanged).
+ * Side effect the reference has and we keep: walk_target stays at the LAST grid cell's stone until the next
+ * delta_to_k_targets.  Envs without the flag return zeros (self.temp_states).  grid = the five fake_* sample arrays. */
+int sso_create_temp_states(sso_env* S, int32_t variant, const double* grid, const double* restore, float* out) {
+    if (!S || !grid || !out || (variant != 1 && variant != 2 && variant != 5)) return SS_ERR_ARG;
+    const ss_model* M = &S->M; const ss_params* P = &S->P;
+    const int g = SS_GRID;
+    const int n3 = variant >= 2 ? g : 1, n45 = variant == 5 ? g : 1;
+    const size_t G = (size_t)g * g * n3 * n45 * n45;
+    for (int i = 0; i < S->n; i++) {
+        env_t* e = &S->e[i];
+        float* o = out + (size_t)i * G * 60;
+        if (!e->update_terrain) { memset(o, 0, G * 60 * sizeof(float)); continue; }
+        int bci = (e->next_step + 1) % P->n_steps;
+        double saved[6]; memcpy(saved, e->terrain + 6 * bci, 48);
+        for (int iy = 0; iy < g; iy++)
+            for (int ip = 0; ip < g; ip++)
+                for (int ir = 0; ir < n3; ir++)
+                    for (int ix = 0; ix < n45; ix++)
+                        for (int it = 0; it < n45; it++) {
+                            double r = variant == 1 ? 0.7 : grid[2 * g + ir];
+                            double xt = variant == 5 ? grid[3 * g + ix] : 0.0, yt = variant == 5 ? grid[4 * g + it] : 0.0;
+                            set_next_next_step_location(P, e, M_PI / 2 - grid[g + ip], grid[iy], r, xt, yt);
+                            calc_state(M, e);                                  /* get_state: mike.py:390-394 */
+                            delta_to_k_targets(P, e);
+                            write_obs(e, o);
+                            o += 60;
+                        }
+        if (restore) set_next_next_step_location(P, e, restore[0], restore[1], restore[2], restore[3], restore[4]);
+        else memcpy(e->terrain + 6 * bci, saved, 48);
+    }
+    return 0;
+}
+
 int sso_set_sample_cdf(sso_env* S, const double* cdf, int32_t n_cells, int32_t apply_now) {
     if (n_cells != SS_GRID_CELLS) return SS_ERR_ARG;
     memcpy(S->cdf, cdf, sizeof(double) * n_cells);

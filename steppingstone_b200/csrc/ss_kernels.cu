@@ -257,16 +257,24 @@ __device__ __forceinline__ void delta_to_k_targets(const DevModel& M, const DevS
     __syncwarp();
 }
 
-// walker3d_envs.py:1245-1274 / mike.py:755-784
+// walker3d_envs.py:1245-1274 / mike.py:755-784: the row set_next_next_step_location writes, from the next stone's row nx
+__device__ __forceinline__ void next_next_row(const DevModel& M, const double* nx, double bphi, double sp, double cp, double sy,
+                                              double cy, double yaw, double dr, double xt, double yt, double* v) {
+    double byaw = nx[3], sb, cb;
+    sincos(byaw, &sb, &cb);
+    double dx = clip_dx(M, dr * sp * cy), dy = dr * sp * sy;
+    v[0] = nx[0] + cb * dx - sb * dy; v[1] = nx[1] + sb * dx + cb * dy; v[2] = nx[2] + dr * cp; v[3] = yaw + byaw; v[4] = xt; v[5] = yt;
+    (void)bphi;
+}
 __device__ __forceinline__ void set_next_next_step_location(const DevModel& M, const DevState& S, int e, const Env& E, int lane,
                                                             double pitch, double yaw, double dr, double xt, double yt) {
     const double* nx = S.terrain + ((size_t)e * M.n_steps + E.next_step) * 6;
     int bci = (E.next_step + 1) % M.n_steps;
-    double bphi = base_phi(M, E.mirrored, bci), byaw = nx[3];
-    double sp, cp, sy, cy, sb, cb;
-    sincos(pitch, &sp, &cp); sincos(yaw + bphi, &sy, &cy); sincos(byaw, &sb, &cb);
-    double dx = clip_dx(M, dr * sp * cy), dy = dr * sp * sy;
-    double v[6] = { nx[0] + cb * dx - sb * dy, nx[1] + sb * dx + cb * dy, nx[2] + dr * cp, yaw + byaw, xt, yt };
+    double bphi = base_phi(M, E.mirrored, bci);
+    double sp, cp, sy, cy;
+    sincos(pitch, &sp, &cp); sincos(yaw + bphi, &sy, &cy);
+    double v[6];
+    next_next_row(M, nx, bphi, sp, cp, sy, cy, yaw, dr, xt, yt, v);
     __syncwarp();
     if (lane == 0) {
         double* t = S.terrain + ((size_t)e * M.n_steps + bci) * 6;
@@ -607,6 +615,109 @@ __global__ void __launch_bounds__(BLOCK) resample_kernel(const DevModel* gm, Dev
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// create_temp_states (walker3d_envs.py:1189-1243 / mike.py:699-753): value-guided sampling probes.
+//   temp_prep_kernel  warp per env: the env's current observation row (get_state + both targets), the context the
+//                     per-cell kernel needs, and the reference's side effects (walk_target left at the LAST grid
+//                     cell; the next-next stone "restored" from next_next_* -- a no-op for Mike, a flattening for W3D)
+//   temp_fill_kernel  block per 256 grid cells of one env: only observation columns 55..59 (the second target)
+//                     depend on the cell; rows are assembled in shared memory and streamed out as float4.
+//                     HBM-write bound: 240 B per (env, cell).
+// ---------------------------------------------------------------------------------------------
+struct TempGrid { double a[5][SS_GRID]; double restore[5]; int variant, has_restore, n3, n45; };
+constexpr int TS_CTX = 12;         // doubles per env: flag, pos xyz, yaw, nx (x y z phi), bphi, modifies-target-1, pad
+constexpr int TS_CELLS = 256;      // cells per block of temp_fill_kernel
+
+__global__ void __launch_bounds__(BLOCK) temp_prep_kernel(const DevModel* gm, DevState S, TempGrid G, float* __restrict__ base,
+                                                          double* __restrict__ ctx) {
+    BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
+    stage_model(B, gm);
+    const DevModel& M = B.M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= S.n) return;
+    WarpSmem& W = B.W[warp];
+    Env E; env_load(S, e, lane, E);
+    double* c = ctx + (size_t)e * TS_CTX;
+    if (!E.update_terrain) { if (lane == 0) c[0] = 0.0; return; }
+    float rpy[3]; int jal; bool fin;
+    calc_state(M, W, E, lane, rpy, jal, fin);                    // get_state: robot.calc_state() on the current pose
+    delta_to_k_targets(M, S, W, e, E, rpy[2], lane);
+    write_obs(W, E, base + (size_t)e * 64, lane);
+    const int bci = (E.next_step + 1) % M.n_steps, idx1 = min(E.next_step + 1, M.n_steps - 1);
+    const double* nx = S.terrain + ((size_t)e * M.n_steps + E.next_step) * 6;
+    const double bphi = base_phi(M, E.mirrored, bci);
+    if (lane == 0) {
+        c[0] = 1.0; c[1] = E.pos[0]; c[2] = E.pos[1]; c[3] = E.pos[2]; c[4] = (double)rpy[2];
+        c[5] = nx[0]; c[6] = nx[1]; c[7] = nx[2]; c[8] = nx[3]; c[9] = bphi; c[10] = idx1 == bci ? 1.0 : 0.0;
+    }
+    // side effects: the last get_temp_state leaves walk_target at the last cell's stone (if that stone is target 1)
+    if (idx1 == bci) {
+        const int g = SS_GRID - 1;
+        double r = G.variant == 1 ? 0.7 : G.a[2][g], xt = G.variant == 5 ? G.a[3][g] : 0.0, yt = G.variant == 5 ? G.a[4][g] : 0.0;
+        double sp, cp, sy, cy, v[6];
+        sincos(SS_PI_D / 2 - G.a[1][g], &sp, &cp); sincos(G.a[0][g] + bphi, &sy, &cy);
+        next_next_row(M, nx, bphi, sp, cp, sy, cy, G.a[0][g], r, xt, yt, v);
+        E.walk[0] = v[0]; E.walk[1] = v[1]; E.walk[2] = v[2];
+    }
+    if (G.has_restore) set_next_next_step_location(M, S, e, E, lane, G.restore[0], G.restore[1], G.restore[2], G.restore[3], G.restore[4]);
+    env_store(S, e, lane, E);
+}
+
+__global__ void __launch_bounds__(TS_CELLS) temp_fill_kernel(const DevModel* gm, TempGrid G, const float* __restrict__ base,
+                                                             const double* __restrict__ ctx, float* __restrict__ out, int cells) {
+    __shared__ __align__(16) float row[64];
+    __shared__ float cellv[TS_CELLS][5];
+    __shared__ double tab[4][SS_GRID];       // sin/cos(pi/2 - pitch), sin/cos(yaw + base_phi)
+    const int e = blockIdx.y, c0 = blockIdx.x * TS_CELLS, t = threadIdx.x;
+    const double* c = ctx + (size_t)e * TS_CTX;
+    const bool on = c[0] != 0.0, mod = c[10] != 0.0;
+    const int ncell = min(TS_CELLS, cells - c0);
+    float4* o4 = reinterpret_cast<float4*>(out + ((size_t)e * cells + c0) * SS_OBS);
+    const int nv = ncell * (SS_OBS / 4);
+    if (!on) {                                // self.temp_states: zeros
+        for (int v = t; v < nv; v += TS_CELLS) __stcs(o4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
+        return;
+    }
+    if (t < 64) row[t] = t < SS_OBS ? base[(size_t)e * 64 + t] : 0.f;
+    if (t >= 64 && t < 64 + SS_GRID) { int i = t - 64; sincos(SS_PI_D / 2 - G.a[1][i], &tab[0][i], &tab[1][i]); }
+    if (t >= 96 && t < 96 + SS_GRID) { int i = t - 96; sincos(G.a[0][i] + c[9], &tab[2][i], &tab[3][i]); }
+    __syncthreads();
+    if (t < ncell) {
+        float* cv = cellv[t];
+        if (!mod) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) cv[i] = row[55 + i];
+        } else {
+            int idx = c0 + t;
+            int it = idx % G.n45; idx /= G.n45;
+            int ix = idx % G.n45; idx /= G.n45;
+            int ir = idx % G.n3; idx /= G.n3;
+            int ip = idx % SS_GRID, iy = idx / SS_GRID;
+            double r = G.variant == 1 ? 0.7 : G.a[2][ir], xt = G.variant == 5 ? G.a[3][ix] : 0.0, yt = G.variant == 5 ? G.a[4][it] : 0.0;
+            const double sp = tab[0][ip], cp = tab[1][ip], sy = tab[2][iy], cy = tab[3][iy];
+            double sb, cb; sincos(c[8], &sb, &cb);
+            const DevModel& M = *gm;
+            double dx = clip_dx(M, r * sp * cy), dy = r * sp * sy;
+            double x = c[5] + cb * dx - sb * dy, y = c[6] + sb * dx + cb * dy, z = c[7] + r * cp;
+            float fx = (float)(x - c[1]), fy = (float)(y - c[2]), fz = (float)(z - c[3]);
+            float ang = atan2f(fy, fx) - (float)c[4], dist = sqrtf(fx * fx + fy * fy), s, co;
+            sincosf(ang, &s, &co);
+            cv[0] = s * dist; cv[1] = co * dist; cv[2] = fz; cv[3] = (float)xt; cv[4] = (float)yt;
+        }
+    }
+    __syncthreads();
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    for (int v = t; v < nv; v += TS_CELLS) {
+        int cell = v / 15, k = v - cell * 15;
+        float4 val;
+        if (k < 13) val = r4[k];
+        else if (k == 13) val = make_float4(row[52], row[53], row[54], cellv[cell][0]);
+        else val = make_float4(cellv[cell][1], cellv[cell][2], cellv[cell][3], cellv[cell][4]);
+        __stcs(o4 + v, val);
+    }
+}
+
 // stand-alone forward-dynamics substep: q [N,28], qd [N,27], tau [N,21] f32 -> q, qd in place (524 B / env-substep)
 __global__ void __launch_bounds__(BLOCK, 3) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
                                                                const float* __restrict__ tau, int n) {
@@ -689,6 +800,7 @@ struct ss_env {
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_epret = nullptr;
     uint8_t *d_done = nullptr, *d_to = nullptr; int32_t* d_eplen = nullptr;
     cudaStream_t own = nullptr;
+    float* ts_base = nullptr; double* ts_ctx = nullptr;      // create_temp_states scratch
 };
 
 static void fill_model(DevModel& D, const ss_model& m, const ss_params& p) {
@@ -739,6 +851,7 @@ static int configure_kernels(size_t smem) {
     CK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(temp_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(aba_substep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockSmemDyn)));
     return 0;
 }
@@ -823,6 +936,7 @@ void ss_destroy(ss_env* E) {
     cudaFreeHost(E->h_act); cudaFreeHost(E->h_obs); cudaFreeHost(E->h_rew); cudaFreeHost(E->h_epret);
     cudaFreeHost(E->h_done); cudaFreeHost(E->h_to); cudaFreeHost(E->h_eplen);
     cudaFree(E->d_act); cudaFree(E->d_obs); cudaFree(E->d_rew); cudaFree(E->d_epret); cudaFree(E->d_done); cudaFree(E->d_to); cudaFree(E->d_eplen);
+    cudaFree(E->ts_base); cudaFree(E->ts_ctx);
     if (E->own) cudaStreamDestroy(E->own);
     delete E;
 }
@@ -912,6 +1026,45 @@ int ss_set_sample_cdf(ss_env* E, const double* cdf, int32_t n_cells, int32_t app
         E->launches++;
         CK(cudaGetLastError());
     }
+    return SS_OK;
+}
+
+int ss_update_tables(ss_env* E, const ss_model* model, const ss_params* params, void* stream) {
+    if (!E || !model || !params) return fail(SS_ERR_ARG, "ss_update_tables: bad argument");
+    if (params->n_steps != E->n_steps || params->rendered != E->rendered)
+        return fail(SS_ERR_ARG, "ss_update_tables: n_steps / rendered are fixed at ss_create (they size the terrain arrays)");
+    if (params->n_substeps < 1 || params->n_substeps > 4) return fail(SS_ERR_ARG, "ss_update_tables: n_substeps must be 1..4");
+    static const int parent_tab[NB] = SS_PARENT_TABLE;
+    for (int i = 0; i < NB; i++)
+        if (model->parent[i] != parent_tab[i]) return fail(SS_ERR_ARG, "ss_update_tables: model topology differs from the compiled-in humanoid tree");
+    CK(cudaSetDevice(E->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaStreamSynchronize(E->own));
+    fill_model(E->hm, *model, *params);
+    CK(cudaMemcpy(E->dm, &E->hm, sizeof(DevModel), cudaMemcpyHostToDevice));
+    return SS_OK;
+}
+
+int64_t ss_temp_state_cells(int32_t variant) {
+    return variant == 1 ? 121 : (variant == 2 ? 1331 : (variant == 5 ? SS_GRID_CELLS : 0));
+}
+
+int ss_create_temp_states(ss_env* E, int32_t variant, const double* grid, const double* restore, float* out_dev, void* stream) {
+    if (!E || !grid || !out_dev || ss_temp_state_cells(variant) == 0) return fail(SS_ERR_ARG, "ss_create_temp_states: bad argument");
+    CK(cudaSetDevice(E->device));
+    if (!E->ts_base) { CK(cudaMalloc(&E->ts_base, (size_t)E->n * 64 * 4)); CK(cudaMalloc(&E->ts_ctx, (size_t)E->n * TS_CTX * 8)); }
+    TempGrid G; memset(&G, 0, sizeof G);
+    memcpy(G.a, grid, sizeof G.a);
+    if (restore) { memcpy(G.restore, restore, sizeof G.restore); G.has_restore = 1; }
+    G.variant = variant; G.n3 = variant >= 2 ? SS_GRID : 1; G.n45 = variant == 5 ? SS_GRID : 1;
+    const int cells = (int)ss_temp_state_cells(variant);
+    cudaStream_t st = (cudaStream_t)stream;
+    temp_prep_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S, G, E->ts_base, E->ts_ctx);
+    CK(cudaGetLastError());
+    dim3 grid2((cells + TS_CELLS - 1) / TS_CELLS, E->n);
+    temp_fill_kernel<<<grid2, TS_CELLS, 0, st>>>(E->dm, G, E->ts_base, E->ts_ctx, out_dev, cells);
+    CK(cudaGetLastError());
+    E->launches += 2;
     return SS_OK;
 }
 

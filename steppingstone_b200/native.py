@@ -74,6 +74,9 @@ _SIGNATURES = {
     "ss_step_host": (ctypes.c_int, [_P] * 8),
     "ss_reset_host": (ctypes.c_int, [_P, _P]),
     "ss_set_sample_cdf": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
+    "ss_update_tables": (ctypes.c_int, [_P, _P, _P, _P]),
+    "ss_temp_state_cells": (ctypes.c_int64, [_I32]),
+    "ss_create_temp_states": (ctypes.c_int, [_P, _I32, _P, _P, _P, _P]),
     "ss_get_state": (ctypes.c_int, [_P, _P]),
     "ss_set_state": (ctypes.c_int, [_P, _P]),
     "ss_enable_substep_trace": (ctypes.c_int, [_P, _I32]),

@@ -141,3 +141,20 @@ def choice_cdf(p):
     cdf = np.cumsum(p)
     cdf /= cdf[-1]
     return np.ascontiguousarray(cdf)
+
+
+def fake_sample_grid():
+    """The five ``fake_*_samples`` axes create_temp_states iterates over (walker3d_envs.py:543-547 = mike.py:86-90):
+    yaw, pitch, r, x_tilt, y_tilt -> [5, 11] float64."""
+    deg = np.pi / 180
+    return np.array([np.linspace(-20, 20, num=11) * deg, np.linspace(-50, 50, num=11) * deg,
+                     np.linspace(0.65, 1.5, num=11), np.linspace(-20, 20, num=11) * deg,
+                     np.linspace(-20, 20, num=11) * deg])
+
+
+def temp_state_restore(robot_kind):
+    """What create_temp_states puts the next-next stone back to (pitch, yaw, dr, x_tilt, y_tilt).  Mike: the values its
+    sampler drew for that stone, i.e. the row is unchanged (None).  Walker3D never runs the sampler
+    (walker3d_envs.py:1083), so its next_next_* are still the reset values (walker3d_envs.py:836-843) and the
+    "restore" flattens the stone: pitch 90 deg, yaw 0, dr 0.8, no tilt."""
+    return None if robot_kind == 1 else np.array([np.pi / 2, 0.0, 0.8, 0.0, 0.0])

@@ -62,8 +62,13 @@ class BatchedStepperEnv:
         self.first_env = int(first_env)
         self.log_dir = log_dir
         self._lib = native.load()
-        self._model = _model.make_model(self.robot_kind)
-        self._params = _model.make_params(self.robot_kind, params, terrain_mode)
+        self._tables = _model.load_tables(self.robot_kind)
+        self._overrides = dict(params or {})
+        self._terrain_mode = terrain_mode
+        self._power = 1.0
+        self._model = _model.make_model(self.robot_kind, self._tables)
+        self._params = _model.make_params(self.robot_kind, self._overrides, terrain_mode)
+        self._fake_grid = seeding.fake_sample_grid()
         self.n_steps, self.rendered = self._params.n_steps, self._params.rendered
         self._max_episode_steps = self._params.max_episode_steps
         self.yaw_samples = np.array(self._params.yaw_samples)
@@ -183,14 +188,84 @@ class BatchedStepperEnv:
     def set_mirror(self, mirror):
         """Env-side no-op in the reference too (walker3d_envs.py:585-586)."""
 
+    # reference attribute -> ss_params field (walker3d_envs.py:487-547 / mike.py:30-90)
+    _ENV_PARAMS = {"done_height": "done_height", "step_radius": "step_radius", "stop_frames": "stop_frames",
+                   "electricity_cost": "electricity_cost", "stall_torque_cost": "stall_torque_cost",
+                   "joints_at_limit_cost": "joints_at_limit_cost", "tilt_limit": "tilt_limit_deg",
+                   "yaw_samples": "yaw_samples", "pitch_samples": "pitch_samples", "r_samples": "r_samples",
+                   "x_tilt_samples": "xtilt_samples", "y_tilt_samples": "ytilt_samples"}
+    _ENV_FAKE = ("fake_yaw_samples", "fake_pitch_samples", "fake_r_samples", "fake_x_tilt_samples", "fake_y_tilt_samples")
+    _ENV_FIXED = ("n_steps", "rendered_step_count", "lookahead", "sample_size", "yaw_sample_size", "pitch_sample_size",
+                  "r_sample_size", "x_tilt_sample_size", "y_tilt_sample_size", "control_step", "llc_frame_skip",
+                  "sim_frame_skip")
+
+    def _push_tables(self):
+        self._model = _model.make_model(self.robot_kind, self._tables)
+        self._params = _model.make_params(self.robot_kind, self._overrides, self._terrain_mode)
+        stream = self._stream() if self.output == "torch" else None
+        native.check(self._lib.ss_update_tables(self._h, ctypes.byref(self._model), ctypes.byref(self._params), stream),
+                     "ss_update_tables")
+        self.yaw_samples = np.array(self._params.yaw_samples)
+        self.pitch_samples = np.array(self._params.pitch_samples)
+
     def set_env_params(self, params_dict):
-        raise NotImplementedError("env parameters are compiled into the device tables: pass params= to the constructor")
+        """EnvBase.set_env_params (env_base.py:73-76) on every env: ``setattr`` for attributes the env has, silently
+        nothing otherwise.  Attributes that size device arrays cannot change after construction and raise."""
+        for k, v in params_dict.items():
+            if k in self._ENV_PARAMS:
+                self._overrides[self._ENV_PARAMS[k]] = (np.asarray(v, dtype=np.float64).tolist() if np.ndim(v) else v)
+            elif k == "r_range":
+                self._overrides["r_max"] = float(np.asarray(v).reshape(-1)[1])
+            elif k in self._ENV_FAKE:
+                self._fake_grid[self._ENV_FAKE.index(k)] = np.asarray(v, dtype=np.float64)
+            elif k in self._ENV_FIXED:
+                raise NotImplementedError("%s is fixed at construction (it sizes the device arrays): pass params= to the constructor" % k)
+        self._push_tables()
 
     def set_robot_params(self, params_dict):
-        raise NotImplementedError("robot parameters are compiled into the device tables: pass params= to the constructor")
+        """EnvBase.set_robot_params (env_base.py:78-85): only ``power`` matters -- the torque limits are recomputed as
+        power * power_coef (robots.py:385-388)."""
+        if "power" in params_dict:
+            base = _model.load_tables(self.robot_kind)["tau_max"]
+            self._power = float(params_dict["power"])
+            self._tables["tau_max"] = base * self._power
+        self._push_tables()
 
-    def create_temp_states(self):
-        raise NotImplementedError("value-guided sampling (mike.py:735-753) is not built yet (SURVEY 8f item 3)")
+    def create_temp_states(self, variant=5):
+        """ShmemVecEnv.create_temp_states (envs_utils.py:573-578) -> [N, G, 60] float32: for every env that advanced a
+        stone in the last step, ``get_temp_state()`` with the next-next stone moved to each cell of the probe grid
+        (mike.py:735-753; ``variant`` 5 = yaw x pitch x r x x_tilt x y_tilt, 161051 cells; 2 = yaw x pitch x r
+        (create_temp_states_2, 1331); 1 = yaw x pitch at r = 0.7 (create_temp_states_1, 121 -- the shape
+        train.py:255-257 views).  Envs that did not advance return zeros (the reference's ``self.temp_states``)."""
+        G = int(self._lib.ss_temp_state_cells(int(variant)))
+        if G == 0:
+            raise ValueError("variant must be 1, 2 or 5")
+        nbytes = self.num_envs * G * OBS_DIM * 4
+        torch = self._torch if self.output == "torch" else __import__("torch")
+        dev = torch.device("cuda", self.device_index)
+        free, _ = torch.cuda.mem_get_info(dev)
+        if nbytes > 0.9 * free:
+            raise MemoryError("create_temp_states(variant=%d) needs %.1f GB for %d envs x %d cells; use variant=1/2 or "
+                              "fewer envs (the reference only calls the 5-D form on a single evaluation env)"
+                              % (variant, nbytes / 1e9, self.num_envs, G))
+        out = torch.empty((self.num_envs, G, OBS_DIM), dtype=torch.float32, device=dev)
+        restore = seeding.temp_state_restore(self.robot_kind)
+        if self.output == "torch":
+            stream = self._stream()
+        else:
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        native.check(self._lib.ss_create_temp_states(self._h, int(variant), self._fake_grid.ctypes.data,
+                                                     None if restore is None else restore.ctypes.data,
+                                                     out.data_ptr(), stream), "ss_create_temp_states")
+        if self.output == "torch":
+            return out
+        return out.cpu().numpy()
+
+    def create_temp_states_1(self):
+        return self.create_temp_states(1)
+
+    def create_temp_states_2(self):
+        return self.create_temp_states(2)
 
     def get_images(self, mode="human"):
         raise NotImplementedError("rendering is out of scope (SURVEY 2, components 6b/16)")

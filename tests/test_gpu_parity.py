@@ -349,3 +349,97 @@ def test_soak_large_actions_stay_finite():
     st = g.get_state()
     assert np.isfinite(st["q"]).all() and np.isfinite(st["qd"]).all() and np.isfinite(st["warm"]).all()
     assert np.allclose(np.linalg.norm(st["q"][:, 3:7], axis=1), 1.0, atol=1e-4)
+
+
+def _force_advance(st, n, count):
+    """make the next env_post advance a stone: a foot contact on the target with the dwell counter one short"""
+    st["ints"][:, 1] = count
+    st["scalars"][:, 14:16] = 1.0
+    tgt = st["terrain"][np.arange(n), st["ints"][:, 0]]
+    st["q"][:, 0:2] = tgt[:, 0:2]; st["q"][:, 2] = tgt[:, 2] + 0.9
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("variant", [1, 2, 5])
+def test_create_temp_states(kind, variant):
+    """create_temp_states_1 / _2 / create_temp_states (value-guided sampling probes): every grid row, the zero rows of
+    envs that did not advance, and the reference's side effects (walk_target, W3D's flattening restore)."""
+    from steppingstone_b200 import seeding
+    n = 6 if variant == 5 else 24
+    o = make_oracle(kind, n); g = make_gpu_env(kind, n)
+    if kind == 1:
+        o.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(5))); g.update_curriculum(5)
+    o.reset(); g.reset()
+    st = o.get_state()
+    _force_advance(st, n, 29)
+    st["ints"][::3, 1] = 3                       # every third env does NOT advance -> zeros
+    rng = np.random.RandomState(4)
+    st["q"][:, 7:] += rng.uniform(-0.1, 0.1, (n, 21)); st["qd"] = rng.randn(n, 27) * 0.3
+    o.set_state(st); g.set_state(st)
+    a = np.zeros((n, 21), np.float32)
+    o.env_post(a); g.env_post(a)
+    ts_o = o.create_temp_states(variant, seeding.fake_sample_grid(), seeding.temp_state_restore(kind))
+    ts_g = g.create_temp_states(variant)
+    assert ts_g.shape == ts_o.shape and ts_g.dtype == np.float32
+    assert not ts_o[::3].any() and not ts_g[::3].any()
+    assert np.abs(ts_o[1]).max() > 0
+    cols = np.ones(60, bool)
+    if kind == 1:
+        cols[6:9] = False
+    assert np.max(np.abs(ts_o - ts_g)[:, :, cols]) < 2e-4
+    so, sg = o.get_state(), g.get_state()
+    assert _maxerr(so["terrain"], sg["terrain"]) < 1e-9
+    assert _maxerr(so["scalars"][:, 1:4], sg["scalars"][:, 1:4]) < 1e-9, "walk_target side effect differs"
+    assert np.array_equal(so["ints"], sg["ints"]) and np.array_equal(so["mt"], sg["mt"])
+    # the torch-mode entry returns the same rows as a CUDA tensor
+    if variant == 1:
+        gd = make_gpu_env(kind, n, output="torch")
+        if kind == 1:
+            gd.update_curriculum(5)
+        gd.reset(); gd.set_state(st); gd.env_post(a)
+        assert np.array_equal(gd.create_temp_states_1().cpu().numpy(), ts_g)
+
+
+def test_create_temp_states_last_stone():
+    """next_step == n_steps - 1: the re-placed row wraps to stone 0, which is not a target -> all rows identical."""
+    from steppingstone_b200 import seeding
+    n = 4
+    o = make_oracle(1, n); g = make_gpu_env(1, n)
+    o.reset(); g.reset()
+    st = o.get_state()
+    st["ints"][:, 0] = 38
+    _force_advance(st, n, 29)
+    o.set_state(st); g.set_state(st)
+    a = np.zeros((n, 21), np.float32)
+    o.env_post(a); g.env_post(a)
+    assert (o.get_state()["ints"][:, 0] == 39).all()
+    ts_o = o.create_temp_states(1, seeding.fake_sample_grid(), None); ts_g = g.create_temp_states(1)
+    cols = np.ones(60, bool); cols[6:9] = False
+    assert np.max(np.abs(ts_o - ts_g)[:, :, cols]) < 2e-4
+    assert np.array_equal(ts_g[:, 0], ts_g[:, 120])
+    assert _maxerr(o.get_state()["scalars"][:, 1:4], g.get_state()["scalars"][:, 1:4]) < 1e-9
+
+
+def test_set_env_and_robot_params():
+    """set_env_params / set_robot_params swap the constant tables in place: same results as an env built with them."""
+    n = 32
+    prm = dict(stop_frames=5, done_height=0.8, electricity_cost=3.0)
+    o = make_oracle(0, n, params=prm)
+    g = make_gpu_env(0, n)
+    g.set_env_params(dict(stop_frames=5, done_height=0.8, electricity_cost=3.0, not_an_attribute=1))
+    o.reset(); g.reset()
+    _advance_oracle(o, 6, seed=2)
+    st = o.get_state(); g.set_state(st)
+    a = random_actions(np.random.RandomState(1), n)
+    obs_o, rew_o, done_o = o.env_post(a); obs_g, rew_g, done_g = g.env_post(a)
+    assert np.array_equal(done_o, done_g) and np.max(np.abs(rew_o - rew_g)) < 2e-3
+    with pytest.raises(NotImplementedError):
+        g.set_env_params(dict(n_steps=50))
+    # power scales the torque limits (robots.py:385-388): one step with power 0.5 == one step with half the action
+    g1 = make_gpu_env(0, n); g2 = make_gpu_env(0, n)
+    g1.set_robot_params(dict(power=0.5))
+    g1.reset(); g2.reset(); g1.set_state(st); g2.set_state(st)
+    g1.enable_substep_trace(True); g2.enable_substep_trace(True)
+    a = random_actions(np.random.RandomState(2), n)
+    g1.step(a); g2.step(0.5 * a)
+    assert _maxerr(g1.substep_trace()[0], g2.substep_trace()[0]) < 1e-6

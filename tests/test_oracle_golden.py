@@ -33,8 +33,13 @@ def _oracle_for(g):
     return o
 
 
+def seeding_restore(kind):
+    from steppingstone_b200 import seeding
+    return seeding.temp_state_restore(kind)
+
+
 def test_golden_files_present():
-    assert len(GOLDEN) >= 8
+    assert len(GOLDEN) >= 10
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -56,12 +61,25 @@ def test_env_logic_matches_reference(path):
     assert np.abs(st["terrain"][0] - terr[0]).max() < 1e-12, "terrain after the first reset"
     T = len(g["rew"])
     n_ep = 0
+    ts_step = list(g["ts_step"]) if "ts_step" in g.files else []
     for t in range(T):
         ob, rew, done, to, er, el = o.step_injected(g["actions"][t][None], g["q"][t][None], g["qd"][t][None], g["contact"][t][None])
         assert bool(done[0]) == bool(g["done"][t]), "done differs at step %d" % t
         assert bool(to[0]) == bool(g["bad"][t]), "bad_transition differs at step %d" % t
         assert abs(float(rew[0]) - g["rew"][t]) < 1e-5 * max(1.0, abs(g["rew"][t])), "reward differs at step %d: ref %r oracle %r" % (t, g["rew"][t], rew[0])
         close(ob[0], g["obs"][t], "obs", t)
+        if t in ts_step:
+            # value-guided sampling probes (create_temp_states_1/_2/create_temp_states, mike.py:699-753): the
+            # reference leaves walk_target at the last grid cell, so the NEXT step's reward checks that too
+            k = ts_step.index(t); variant = int(g["ts_variant"][k])
+            ts = o.create_temp_states(variant, g["ts_grid"], seeding_restore(kind))[0]
+            ref = g["ts_%d" % k]
+            if variant == 5:
+                assert np.abs(ts.astype(np.float64).sum(axis=0) - g["ts_sum_%d" % k]).max() < 2e-6 * 161051 * 5
+                ts = ts[::1009]
+            assert ts.shape == ref.shape
+            err = np.abs(ts.astype(np.float64) - ref) / (scale * np.maximum(1.0, np.abs(ref)))
+            assert err.max() < 2e-6, "temp states (variant %d) differ at step %d: %r" % (variant, t, err.max())
         if done[0]:
             n_ep += 1
             assert int(el[0]) == int(g["ep_l"][t])

@@ -118,8 +118,10 @@ class RefWorker:
         return np.asarray(ob, dtype=np.float32), float(r), bool(d), info, internals
 
 
-def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=None, curriculum=None, oracle_params=None):
-    """tape_fn(t, worker, sim) -> (q, qd, contact) for step t."""
+def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=None, curriculum=None, oracle_params=None,
+           temp_states=False):
+    """tape_fn(t, worker, sim) -> (q, qd, contact) for step t.  temp_states: after every step that advanced a stone
+    call the reference's create_temp_states_1 / _2 / create_temp_states (value-guided sampling probes) and record them."""
     fk = make_oracle(kind, seed)
     w = RefWorker(kind, seed, fk, time_limit, env_params, curriculum)
     rec = dict(kind=kind, seed=seed, time_limit=time_limit or 0, curriculum=-1 if curriculum is None else curriculum,
@@ -127,6 +129,7 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
     obs0 = w.reset()
     terr = [w.env.terrain_info.copy()]; terr_at = [-1]
     Q, QD, C, OBS, REW, DONE, BAD, EPR, EPL, NXT, CNT, POT = ([] for _ in range(12))
+    ts_step, ts_variant, ts_data = [], [], {}
     for t in range(T):
         q, qd, c = tape_fn(t, w)
         ob, r, d, info, (nxt, cnt, pot) = w.step(actions[t], q, qd, c)
@@ -135,6 +138,17 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
         EPR.append(info["episode"]["r"] if "episode" in info else 0.0)
         EPL.append(info["episode"]["l"] if "episode" in info else 0)
         NXT.append(nxt); CNT.append(cnt); POT.append(pot)
+        if temp_states and not d and w.env.update_terrain:
+            k = len(ts_step)
+            variant = 5 if k == 2 else (2 if k % 4 == 1 and k < 10 else 1)
+            fn = {1: w.env.create_temp_states_1, 2: w.env.create_temp_states_2, 5: w.env.create_temp_states}[variant]
+            ts = np.asarray(fn())
+            ts_step.append(t); ts_variant.append(variant)
+            if variant == 5:                                   # 161051 x 60: keep a strided sample + column sums
+                ts_data["ts_%d" % k] = ts[::1009].astype(np.float32)
+                ts_data["ts_sum_%d" % k] = ts.sum(axis=0)
+            else:
+                ts_data["ts_%d" % k] = ts.astype(np.float32)
         if d or t == T - 1 or (t % 97 == 0):
             terr.append(w.env.terrain_info.copy()); terr_at.append(t)
     rec.update(actions=np.asarray(actions[:T], np.float32), q=np.array(Q), qd=np.array(QD), contact=np.array(C),
@@ -142,6 +156,11 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
                ep_r=np.array(EPR), ep_l=np.array(EPL, np.int32), next_step=np.array(NXT, np.int32),
                reached_count=np.array(CNT, np.int32), potential=np.array(POT),
                terrain=np.array(terr), terrain_at=np.array(terr_at, np.int32))
+    if temp_states:
+        e = w.env
+        rec.update(ts_step=np.array(ts_step, np.int32), ts_variant=np.array(ts_variant, np.int32),
+                   ts_grid=np.array([e.fake_yaw_samples, e.fake_pitch_samples, e.fake_r_samples, e.fake_x_tilt_samples,
+                                     e.fake_y_tilt_samples]), **ts_data)
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     print("%-28s T=%d episodes=%d max next_step=%d reward[min,max]=[%.2f, %.2f]" % (
@@ -214,6 +233,11 @@ def main():
         acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)
         record("%s_ghost_laststone" % nm, kind, 12, acts, ghost_tape(kind, 12, rng, 6), T, time_limit=None,
                env_params={"stop_frames": 5}, curriculum=(3 if kind == 1 else None))
+        T = 150
+        rng = np.random.RandomState(55 + kind)
+        acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)
+        record("%s_ghost_tempstates" % nm, kind, 13, acts, ghost_tape(kind, 13, rng, 6), T, time_limit=None,
+               env_params={"stop_frames": 5}, curriculum=(5 if kind == 1 else None), temp_states=True)
 
 
 if __name__ == "__main__":

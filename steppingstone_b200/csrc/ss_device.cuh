@@ -28,7 +28,6 @@ constexpr int NB = SS_NB, NJ = SS_NJ, ND = SS_NDOF;
 constexpr int HS = 28;   // row stride of H / L in shared memory: 16-byte aligned rows; a lane reads ITS row with 7 LDS.128
                          // (quarter-warp addresses 112 B apart hit disjoint bank groups -> conflict-free)
 constexpr int ZS = 28;   // row stride of Z (same access pattern)
-constexpr int AS = 33;   // row stride of A
 constexpr int MAXC = SS_MAX_CONTACTS, MAXL = SS_MAX_LIMIT_ROWS;
 
 // ---------------------------------------------------------------------------------------------
@@ -80,10 +79,12 @@ struct alignas(16) WarpSmem {
     float lim[MAXL][4];       // hinge, dir, penetration
     float dinv[32];
     union {
-        struct { float H[HS * HS]; float Z[32 * ZS]; float A[32 * AS]; } s;
-        double d[(HS * HS + 32 * ZS + 32 * AS) / 2];
+        struct { float H[HS * HS]; float Z[32 * ZS]; } s;
+        double d[(HS * HS + 32 * ZS) / 2];
     } u;
 };
+
+static_assert(sizeof(((WarpSmem*)0)->u.d) >= 7 * SS_MAX_STONES * sizeof(double), "terrain generator scratch (7 arrays of n_steps doubles) must fit the per-warp union");
 
 // scratch of the dynamics-only kernel (aba_substep): same member names, no constraint-solver storage
 struct alignas(16) WarpSmemDyn {
@@ -598,36 +599,43 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         if (lane < ND) W.vec[lane] = vs;
         __syncwarp();
 
-        // ---- lane = row: Jacobian row, z = L^-1 J^T ----
+        // ---- lane = row slot: Jacobian row, z = L^-1 J^T ----
+        // Fixed slots (compile-time row indices in the solver): 0..7 contact normals, 8..23 friction (two per contact,
+        // contact-major as Bullet orders them), 24..31 violated hinge limits.  Inactive slots carry all-zero rows.
         const int r = lane;
         float z[HS];
 #pragma unroll
         for (int k = 0; k < HS; k++) z[k] = 0.f;
         int rtype = -1;      // 0 limit, 1 normal, 2/3 friction
         int nidx = -1; float pen = 0.f, lam = 0.f;
-        if (r < nl) {
-            rtype = 0;
-            int hj = (int)W.lim[r][0]; float dir = W.lim[r][1]; pen = W.lim[r][2];
+        {
+            int c = -1, a = 0;
+            if (r < MAXC) { if (r < nc) c = r; }
+            else if (r < 3 * MAXC) { int cc = (r - MAXC) >> 1; if (cc < nc) { c = cc; a = 1 + ((r - MAXC) & 1); nidx = cc; } }
+            else if (r - 3 * MAXC < nl) {
+                rtype = 0;
+                const float* ld = W.lim[r - 3 * MAXC];
+                int hj = (int)ld[0]; float dir = ld[1]; pen = ld[2];
 #pragma unroll
-            for (int k = 6; k < ND; k++) z[k] = (k - 6 == hj) ? dir : 0.f;
-        } else if (r < nr) {
-            int c, a;
-            if (r < nl + nc) { c = r - nl; a = 0; } else { c = (r - nl - nc) >> 1; a = 1 + ((r - nl - nc) & 1); nidx = nl + c; }
-            rtype = 1 + a;
-            const float* cd = W.con[c];
-            float n[3] = { cd[0], cd[1], cd[2] }, x[3] = { cd[3], cd[4], cd[5] }, dir[3], t1[3], t2[3];
-            plane_space(n, t1, t2);
+                for (int k = 6; k < ND; k++) z[k] = (k - 6 == hj) ? dir : 0.f;
+            }
+            if (c >= 0) {
+                rtype = 1 + a;
+                const float* cd = W.con[c];
+                float n[3] = { cd[0], cd[1], cd[2] }, x[3] = { cd[3], cd[4], cd[5] }, dir[3], t1[3], t2[3];
+                plane_space(n, t1, t2);
 #pragma unroll
-            for (int i = 0; i < 3; i++) dir[i] = a == 0 ? n[i] : (a == 1 ? t1[i] : t2[i]);
-            pen = cd[6]; if (a == 0) lam = cd[9] * M.warmstart;
-            float wr[3]; cross3(x, dir, wr);
-            z[0] = wr[0]; z[1] = wr[1]; z[2] = wr[2]; z[3] = dir[0]; z[4] = dir[1]; z[5] = dir[2];
-            int mask = M.anc_mask[(int)cd[7]];
+                for (int i = 0; i < 3; i++) dir[i] = a == 0 ? n[i] : (a == 1 ? t1[i] : t2[i]);
+                pen = cd[6]; if (a == 0) lam = cd[9] * M.warmstart;
+                float wr[3]; cross3(x, dir, wr);
+                z[0] = wr[0]; z[1] = wr[1]; z[2] = wr[2]; z[3] = dir[0]; z[4] = dir[1]; z[5] = dir[2];
+                int mask = M.anc_mask[(int)cd[7]];
 #pragma unroll
-            for (int i = 1; i < NB; i++) {
-                const float* Si = W.S[i];
-                float v = Si[0] * wr[0] + Si[1] * wr[1] + Si[2] * wr[2] + Si[3] * dir[0] + Si[4] * dir[1] + Si[5] * dir[2];
-                z[5 + i] = ((mask >> i) & 1) ? v : 0.f;
+                for (int i = 1; i < NB; i++) {
+                    const float* Si = W.S[i];
+                    float v = Si[0] * wr[0] + Si[1] * wr[1] + Si[2] * wr[2] + Si[3] * dir[0] + Si[4] * dir[1] + Si[5] * dir[2];
+                    z[5 + i] = ((mask >> i) & 1) ? v : 0.f;
+                }
             }
         }
         // relative velocity along the row before the solve: J v*
@@ -677,18 +685,42 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 hi = 1e10f;
             } else rhs = -rel * invD;
         }
-        // Delassus row, scaled by this row's 1/(D + cfm):  At[r][s] = (w_r . z_s) * invD_r
-        float* A = W.u.s.A;
-        for (int s = 0; s < nr; s++) {
-            const float4* Zs = reinterpret_cast<const float4*>(Z + s * ZS);
-            float a = 0.f;
+        const float omc = 1.f - cfmt;
+        // Delassus row, scaled by this row's 1/(D + cfm):  A[r][s] = (w_r . z_s) * invD_r ; the solver works on
+        // c_r = lam_r (1 - cfm_r) + rhs_r - (J_r dv) invD_r, so the diagonal carries the extra -(1 - cfm_r).
+        // The row stays in REGISTERS (every solver index is a compile-time constant): slots are visited in groups of
+        // four -- normals {0-3, 4-7}, friction {8-11, ...}, limits {24-27, 28-31} -- and groups without a live row are skipped.
+        float Ar[32];
 #pragma unroll
-            for (int j = 0; j < ZS / 4; j++) {
-                float4 v = Zs[j];
-                a = fmaf(z[4 * j], v.x, a); a = fmaf(z[4 * j + 1], v.y, a); a = fmaf(z[4 * j + 2], v.z, a);
-                if (4 * j + 3 < ND) a = fmaf(z[4 * j + 3], v.w, a);
+        for (int k = 0; k < 32; k++) Ar[k] = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 8; g++) {
+            const bool on = g < 2 ? nc > 4 * g : (g < 6 ? nc > 2 * (g - 2) : nl > 4 * (g - 6));
+            if (!on) continue;
+            float a4[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int sl = 4 * g + jj;
+                const float4* Zs = reinterpret_cast<const float4*>(Z + sl * ZS);
+                float a = 0.f;
+#pragma unroll
+                for (int j = 0; j < ZS / 4; j++) {
+                    float4 v = Zs[j];
+                    a = fmaf(z[4 * j], v.x, a); a = fmaf(z[4 * j + 1], v.y, a); a = fmaf(z[4 * j + 2], v.z, a);
+                    if (4 * j + 3 < ND) a = fmaf(z[4 * j + 3], v.w, a);
+                }
+                a4[jj] = a * invD - (sl == r && rtype >= 0 ? omc : 0.f);
             }
-            A[r * AS + s] = a * invD;
+            switch (g) {
+                case 0: Ar[0] = a4[0]; Ar[1] = a4[1]; Ar[2] = a4[2]; Ar[3] = a4[3]; break;
+                case 1: Ar[4] = a4[0]; Ar[5] = a4[1]; Ar[6] = a4[2]; Ar[7] = a4[3]; break;
+                case 2: Ar[8] = a4[0]; Ar[9] = a4[1]; Ar[10] = a4[2]; Ar[11] = a4[3]; break;
+                case 3: Ar[12] = a4[0]; Ar[13] = a4[1]; Ar[14] = a4[2]; Ar[15] = a4[3]; break;
+                case 4: Ar[16] = a4[0]; Ar[17] = a4[1]; Ar[18] = a4[2]; Ar[19] = a4[3]; break;
+                case 5: Ar[20] = a4[0]; Ar[21] = a4[1]; Ar[22] = a4[2]; Ar[23] = a4[3]; break;
+                case 6: Ar[24] = a4[0]; Ar[25] = a4[1]; Ar[26] = a4[2]; Ar[27] = a4[3]; break;
+                default: Ar[28] = a4[0]; Ar[29] = a4[1]; Ar[30] = a4[2]; Ar[31] = a4[3]; break;
+            }
         }
         __syncwarp();
         // overwrite Z with w for the final velocity update
@@ -697,53 +729,69 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
 #pragma unroll
             for (int j = 0; j < ZS / 4; j++) Zr[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
         }
-        // g_r = rhs_r - (J_r dv) invD_r, maintained incrementally; warm start: dv = sum_s W_s lam_s
-        float g = rhs;
-        for (int s = nl; s < nl + nc; s++) { float ls = shfl(lam, s); g = fmaf(-A[r * AS + s], ls, g); }
         if (dbg) {
             dbg[DBG_ROWS + 0] = (float)nl; dbg[DBG_ROWS + 1] = (float)nc;
             float* d = dbg + DBG_ROWS + 4 + lane * 6;
             d[0] = (float)rtype; d[1] = invD; d[2] = rhs; d[3] = rel; d[4] = diag; d[5] = lam;
-            for (int s = 0; s < 32; s++) dbg[DBG_ROWS + 4 + 32 * 6 + lane * 32 + s] = (s < nr && lane < nr) ? A[r * AS + s] : 0.f;
         }
-#if SS_SYNC >= 3
-        __syncwarp();
-#endif
         // ---- projected Gauss-Seidel in constraint space (btMultiBodyConstraintSolver::solveSingleIteration order:
         //      limit rows in alternating direction, then all normals, then all friction rows).
         //      Every lane evaluates its own row update each row-step (branch-free); the owner of row rr publishes its
-        //      impulse change with one shuffle and all lanes fold it into their J.dv accumulator.  Friction bounds
-        //      depend on the normal impulse, which only changes in the normal block: one shuffle per iteration.
+        //      impulse change with one shuffle and all lanes fold it into their accumulator c (5 ops + 1 shuffle, the
+        //      Delassus entry is a register).  Friction bounds depend on the normal impulse, which only changes in the
+        //      normal block: one shuffle per iteration.
         const bool isfric = nidx >= 0;
         const int nsrc = isfric ? nidx : lane;
         const float mu = M.friction;
-        const float omc = 1.f - cfmt;
-        const float* Arow = A + r * AS;
         // friction rows start dead (bounds pinned to the current impulse => no change) until their normal pushes
         float lo_c = isfric ? lam : lo, hi_c = isfric ? lam : hi;
-        auto row_step = [&](int rr) {
-            float sum = fminf(fmaxf(fmaf(lam, omc, g), lo_c), hi_c);     // lam + (rhs - lam cfm - J dv invD), clamped
-            float dl = shfl(sum - lam, rr);
-            if (lane == rr) lam = sum;
-            g = fmaf(-Arow[rr], dl, g);
-        };
+        float c = rhs;
+#define SS_ROW_STEP(RR)                                                        \
+        {                                                                      \
+            float sum_ = fminf(fmaxf(c, lo_c), hi_c);                          \
+            float dl_ = shfl(sum_ - lam, (RR));                                \
+            lam = (lane == (RR)) ? sum_ : lam;                                 \
+            c = fmaf(-Ar[(RR)], dl_, c);                                       \
+        }
+        // warm start: fold the cached normal impulses in (dv = sum_s W_s lam_s)
+#pragma unroll
+        for (int k = 0; k < MAXC; k += 2)
+            if (nc > k) {
+                float l0 = shfl(lam, k), l1 = shfl(lam, k + 1);
+                c = fmaf(-Ar[k], l0, c); c = fmaf(-Ar[k + 1], l1, c);
+            }
         for (int it = 0; it < M.n_iters; it++) {
-            if (it & 1) { for (int s = 0; s < nl; s++) row_step(s); }
-            else { for (int s = nl - 1; s >= 0; s--) row_step(s); }
-#pragma unroll 4
-            for (int rr = nl; rr < nl + nc; rr++) row_step(rr);
+            if (it & 1) {
+#pragma unroll
+                for (int k = 0; k < MAXL; k += 2)
+                    if (nl > k) { SS_ROW_STEP(3 * MAXC + k); SS_ROW_STEP(3 * MAXC + k + 1); }
+            } else {
+#pragma unroll
+                for (int k = MAXL - 2; k >= 0; k -= 2)
+                    if (nl > k) { SS_ROW_STEP(3 * MAXC + k + 1); SS_ROW_STEP(3 * MAXC + k); }
+            }
+#pragma unroll
+            for (int k = 0; k < MAXC; k += 2)
+                if (nc > k) { SS_ROW_STEP(k); SS_ROW_STEP(k + 1); }
             float ln = shfl(lam, nsrc);
             if (isfric) { bool live = ln > 0.f; hi_c = live ? mu * ln : lam; lo_c = live ? -hi_c : lam; }
-#pragma unroll 4
-            for (int rr = nl + nc; rr < nr; rr++) row_step(rr);
+#pragma unroll
+            for (int k = 0; k < MAXC; k += 2)
+                if (nc > k) {
+                    SS_ROW_STEP(MAXC + 2 * k); SS_ROW_STEP(MAXC + 2 * k + 1); SS_ROW_STEP(MAXC + 2 * k + 2); SS_ROW_STEP(MAXC + 2 * k + 3);
+                }
         }
+#undef SS_ROW_STEP
         if (dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
         // ---- velocity update: dv = L^-T sum_r w_r lam_r ----
         float u = 0.f;
-        for (int s = 0; s < nr; s++) { float ls = shfl(lam, s); if (lane < ND) u += Z[s * ZS + lane] * ls; }
+        auto gather = [&](int s0, int s1) {
+            for (int s = s0; s < s1; s++) { float ls = shfl(lam, s); if (lane < ND) u = fmaf(Z[s * ZS + lane], ls, u); }
+        };
+        gather(0, nc); gather(MAXC, MAXC + 2 * nc); gather(3 * MAXC, 3 * MAXC + nl);
         dv = solve_lt(W, u, lane);
         // warm-start cache: candidate lane reads its normal row's impulse
-        float lw = shfl(lam, (nl + cidx) & 31);
+        float lw = shfl(lam, cidx & (MAXC - 1));
         newwarm = active ? lw : 0.f;
         __syncwarp();
     }

@@ -17,10 +17,13 @@ namespace ssb {
 // thrash the instruction caches (ncu: stall_no_instruction was the top stall).  8 warps per CTA re-aligned by one
 // __syncthreads() per substep share their instruction fetches: 7.2M -> 10.2M env-steps/s at N=8192 (profiles/).
 #ifndef SS_WPB
-#define SS_WPB 8
+#define SS_WPB 10
 #endif
 #ifndef SS_SYNC
 #define SS_SYNC 1
+#endif
+#ifndef SS_MINB
+#define SS_MINB 2
 #endif
 constexpr int WARPS_PER_BLOCK = SS_WPB;
 constexpr int BLOCK = 32 * WARPS_PER_BLOCK;
@@ -306,37 +309,31 @@ __device__ __forceinline__ void update_terrain_info(const DevModel& M, const Dev
     delta_to_k_targets(M, S, W, e, E, yaw, lane);
 }
 
-// walker3d_envs.py:624-755 (W3D) / mike.py:167-276 (Mike).  Scratch: W.u.d (>= 13 * n_steps doubles).
+// walker3d_envs.py:624-755 (W3D) / mike.py:167-276 (Mike).  Scratch: W.u.d (>= 7 * n_steps doubles).
+// Only dr is a genuine random array: the yaw / pitch / tilt draws are `uniform(a, a)` = a + 0 * u = a exactly, so they are
+// consumed from the stream (the seed-exact draw order matters) but not stored.
 __device__ __forceinline__ void generate_step_placements(const DevModel& M, const DevState& S, WarpSmem& W, int e, Env& E, int lane) {
     const int n = M.n_steps;
-    double* dr = W.u.d; double *dphi = dr + n, *dth = dr + 2 * n, *xt = dr + 3 * n, *yt = dr + 4 * n, *cphi = dr + 5 * n,
-            *X = dr + 6 * n, *Y = dr + 7 * n, *Z = dr + 8 * n, *U = dr + 9 * n, *YAW = dr + 10 * n, *PHI = dr + 11 * n;
+    double* dr = W.u.d; double *cphi = dr + n, *X = dr + 2 * n, *Y = dr + 3 * n, *Z = dr + 4 * n, *U = dr + 5 * n, *PHI = dr + 6 * n;
     uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
     double* T = S.terrain + (size_t)e * n * 6;
     const bool mike = M.terrain_mode == 1;
     const double dr_lo = 0.65, dr_hi = mike ? 0.65 : 0.8, y0 = mike ? -10 * SS_DEG_D : 0.0, t0 = mike ? -20 * SS_DEG_D : 0.0;
+    auto dphi_of = [&](int i) { return i < 3 ? 0.0 : y0; };
+    auto dth_of = [&](int i) { return i < 3 ? SS_PI_D / 2 : 90 * SS_DEG_D; };
     __syncwarp();
     mt_doubles_warp(mt, E.mtpos, dr, n, lane);
-    mt_doubles_warp(mt, E.mtpos, dphi, n, lane);
-    mt_doubles_warp(mt, E.mtpos, dth, n, lane);
-    mt_doubles_warp(mt, E.mtpos, xt, n, lane);
-    mt_doubles_warp(mt, E.mtpos, yt, n, lane);
+    mt_doubles_warp(mt, E.mtpos, nullptr, 4 * n, lane);          // dphi, dtheta, x_tilt, y_tilt draws
     for (int i = lane; i < n; i += 32) {
         dr[i] = dr_lo + (dr_hi - dr_lo) * dr[i];
-        dphi[i] = y0 + (y0 - y0) * dphi[i];
-        dth[i] = 90 * SS_DEG_D + (90 * SS_DEG_D - 90 * SS_DEG_D) * dth[i];
-        xt[i] = t0 + (t0 - t0) * xt[i];
-        yt[i] = 0.0 + 0.0 * yt[i];
-        if (i < 3) {
-            dr[i] = i == 0 ? 0.0 : (i == 1 ? 0.8 : 0.75); dphi[i] = 0.0; dth[i] = SS_PI_D / 2; xt[i] = 0.0; yt[i] = 0.0;
-        }
+        if (i < 3) dr[i] = i == 0 ? 0.0 : (i == 1 ? 0.8 : 0.75);
     }
     __syncwarp();
-    if (lane == 0) { double acc = 0; for (int i = 0; i < n; i++) { acc += dphi[i]; cphi[i] = acc; } }
+    if (lane == 0) { double acc = 0; for (int i = 0; i < n; i++) { acc += dphi_of(i); cphi[i] = acc; } }
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
         double bp = base_phi(M, E.mirrored, i), st, ct, sp, cp;
-        sincos(dth[i], &st, &ct); sincos(cphi[i] + bp, &sp, &cp);
+        sincos(dth_of(i), &st, &ct); sincos(cphi[i] + bp, &sp, &cp);
         double x_ = dr[i] * st * cp;
         if (i >= 2) x_ = clip_dx(M, x_);
         X[i] = x_; Y[i] = dr[i] * st * sp; Z[i] = dr[i] * ct;
@@ -348,7 +345,7 @@ __device__ __forceinline__ void generate_step_placements(const DevModel& M, cons
         for (int i = 0; i < n; i++) {
             ax += X[i]; ay += Y[i]; az += Z[i];
             double* t = T + 6 * i;
-            t[0] = ax; t[1] = ay; t[2] = fmax(az + 0, min_z); t[3] = cphi[i]; t[4] = xt[i]; t[5] = yt[i];
+            t[0] = ax; t[1] = ay; t[2] = fmax(az + 0, min_z); t[3] = cphi[i]; t[4] = i < 3 ? 0.0 : t0; t[5] = 0.0;
         }
     }
     __syncwarp();
@@ -357,7 +354,7 @@ __device__ __forceinline__ void generate_step_placements(const DevModel& M, cons
     for (int i = 2 + lane; i < n - 1; i += 32) {
         int bci = i + 1;
         double bphi = base_phi(M, E.mirrored, bci);
-        double pitch = dth[bci], yaw = dphi[bci];
+        double pitch = dth_of(bci), yaw = dphi_of(bci);
         if (!mike) {
             pitch = (i % 2 == 0) ? 120 * SS_DEG_D : 60 * SS_DEG_D;
             if (U[i] < 0.2) pitch = 90 * SS_DEG_D;
@@ -365,10 +362,10 @@ __device__ __forceinline__ void generate_step_placements(const DevModel& M, cons
         }
         double sp, cp, sy, cy;
         sincos(pitch, &sp, &cp); sincos(yaw + bphi, &sy, &cy);
-        X[i] = clip_dx(M, dr[bci] * sp * cy); Y[i] = dr[bci] * sp * sy; Z[i] = dr[bci] * cp; YAW[i] = yaw;
+        X[i] = clip_dx(M, dr[bci] * sp * cy); Y[i] = dr[bci] * sp * sy; Z[i] = dr[bci] * cp;
     }
     __syncwarp();
-    if (lane == 0) { PHI[2] = cphi[2]; for (int i = 2; i < n - 1; i++) PHI[i + 1] = YAW[i] + PHI[i]; }
+    if (lane == 0) { PHI[2] = cphi[2]; for (int i = 2; i < n - 1; i++) PHI[i + 1] = dphi_of(i + 1) + PHI[i]; }
     __syncwarp();
     for (int i = 2 + lane; i < n - 1; i += 32) {
         double sb, cb; sincos(PHI[i], &sb, &cb);
@@ -475,7 +472,7 @@ __device__ __forceinline__ void setup_stones(const DevModel& M, const DevState& 
 // ---------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-__global__ void __launch_bounds__(BLOCK) env_step_kernel(const DevModel* gm, DevState S, const float* __restrict__ act,
+__global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel* gm, DevState S, const float* __restrict__ act,
                                                          float* __restrict__ obs, float* __restrict__ rew,
                                                          uint8_t* __restrict__ done, uint8_t* __restrict__ timeout,
                                                          float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int physics) {

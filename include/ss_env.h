@@ -81,9 +81,12 @@ int ss_reset_all(ss_env* env, float* obs_dev, void* stream);
 int ss_step(ss_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
             uint8_t* timeout_dev, float* ep_ret_dev, int32_t* ep_len_dev, void* stream);
 
-/* Same call with HOST buffers (the reference's numpy-in / numpy-out contract): copies actions in,
- * steps, copies the five result arrays out through pinned staging, and synchronises. */
-int ss_step_host(ss_env* env, const float* act_host, float* obs_host, float* rew_host,
+/* Same call with HOST buffers (the reference's numpy-in / numpy-out contract, envs_utils.py:550-558, 608-620):
+ * rew_host is float64 like the reference's stacked python floats, done_host / timeout_host are 0/1 bytes (numpy
+ * bool storage).  Non-finite actions fail with SS_ERR_ARG before anything runs (robots.py:290).  Internally the batch
+ * is pipelined in slices (H2D -> kernel -> one packed D2H per slice, unpacked on the host while later slices run);
+ * returns after everything has landed in the caller's arrays. */
+int ss_step_host(ss_env* env, const float* act_host, float* obs_host, double* rew_host,
                  uint8_t* done_host, uint8_t* timeout_host, float* ep_ret_host, int32_t* ep_len_host);
 int ss_reset_host(ss_env* env, float* obs_host);
 
@@ -144,6 +147,9 @@ int32_t ss_debug_floats(void);
 int ss_enable_debug(ss_env* env, int32_t on);
 int ss_debug_read(ss_env* env, float* out_host);
 
+/* host-side breakdown of the last ss_step_host (seconds): out4 = action copy + finite check, enqueue, waiting on the
+ * device, unpacking result records (bench.py reports it next to e2e) */
+int ss_host_timing(const ss_env* env, double* out4);
 int32_t ss_num_envs(const ss_env* env);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ss_launch_count(const ss_env* env);

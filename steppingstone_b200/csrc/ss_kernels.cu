@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 namespace ssb {
 
@@ -26,6 +27,7 @@ namespace ssb {
 #define SS_MINB 2
 #endif
 constexpr int WARPS_PER_BLOCK = SS_WPB;
+constexpr int SS_REC = 64;       // floats per env in the packed result record of the host-buffer path
 constexpr int BLOCK = 32 * WARPS_PER_BLOCK;
 
 struct alignas(16) BlockSmem {
@@ -475,17 +477,21 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel* gm, DevState S, const float* __restrict__ act,
                                                          float* __restrict__ obs, float* __restrict__ rew,
                                                          uint8_t* __restrict__ done, uint8_t* __restrict__ timeout,
-                                                         float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int physics) {
+                                                         float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int physics,
+                                                         int e_begin, int e_end, float* __restrict__ packed) {
+    // envs [e_begin, e_end) of the batch (the host-buffer entry point pipelines the batch in slices).  packed != null:
+    // results go to one 256-byte record per env -- obs 60 f32, reward, episode return, episode length (int bits),
+    // done | timeout << 8 (int bits) -- so that a slice leaves the device in ONE copy.
     BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
     stage_model(B, gm);
     const DevModel& M = B.M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e_raw = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int e_raw = e_begin + blockIdx.x * WARPS_PER_BLOCK + warp;
 #if SS_SYNC
-    const bool ghost = e_raw >= S.n;            // keeps hitting the block barriers, stores nothing
-    const int e = ghost ? S.n - 1 : e_raw;
+    const bool ghost = e_raw >= e_end;          // keeps hitting the block barriers, stores nothing
+    const int e = ghost ? e_end - 1 : e_raw;
 #else
-    if (e_raw >= S.n) return;
+    if (e_raw >= e_end) return;
     const bool ghost = false;
     const int e = e_raw;
 #endif
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     float r = progress - energy;
     r += step_bonus + target_bonus - 0.f;
     r += tall - posture - joints_pen;
-    float* o = obs + (size_t)e * SS_OBS;
+    float* o = packed ? packed + (size_t)e * SS_REC : obs + (size_t)e * SS_OBS;
     write_obs(W, E, o, lane);
     if (!physics) {
         if (lane == 0) { rew[e] = r; done[e] = dn ? 1 : 0; }
@@ -580,9 +586,13 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     bool d = dn || E.elapsed >= M.max_episode_steps;
     E.ep_ret += (double)r; E.ep_len++;
     if (lane == 0) {
-        rew[e] = r; done[e] = d ? 1 : 0;
-        timeout[e] = (d && E.elapsed == M.max_episode_steps) ? 1 : 0;
-        ep_ret[e] = (float)(rint(E.ep_ret * 1e6) / 1e6); ep_len[e] = E.ep_len;
+        const int to = (d && E.elapsed == M.max_episode_steps) ? 1 : 0;
+        const float er = (float)(rint(E.ep_ret * 1e6) / 1e6);
+        if (packed) {
+            o[SS_OBS] = r; o[SS_OBS + 1] = er; o[SS_OBS + 2] = __int_as_float(E.ep_len); o[SS_OBS + 3] = __int_as_float((d ? 1 : 0) | (to << 8));
+        } else {
+            rew[e] = r; done[e] = d ? 1 : 0; timeout[e] = to; ep_ret[e] = er; ep_len[e] = E.ep_len;
+        }
     }
     env_store(S, e, lane, E);
     if (d) { __syncwarp(); env_reset_from_memory(&M, &S, &W, e, o, lane); }         // envs_utils.py:646-649
@@ -782,6 +792,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(SS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+constexpr int SS_PIPE = 4;        // slices per step of ss_step_host
+
 struct ss_env {
     int n = 0, device = 0, n_steps = 0, rendered = 0;
     DevModel hm;
@@ -791,12 +803,11 @@ struct ss_env {
     int64_t launches = 0;
     size_t smem = 0;
     bool trace = false, debug = false;
-    // pinned staging for the host-buffer entry points
-    float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_epret = nullptr;
-    uint8_t *h_done = nullptr, *h_to = nullptr; int32_t* h_eplen = nullptr;
-    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_epret = nullptr;
-    uint8_t *d_done = nullptr, *d_to = nullptr; int32_t* d_eplen = nullptr;
+    // host-buffer entry points: pinned staging + a pipeline of env slices on separate streams
+    float *h_act = nullptr, *h_rec = nullptr, *d_act = nullptr, *d_rec = nullptr;     // [N,21], [N,64]
     cudaStream_t own = nullptr;
+    cudaStream_t pipe[SS_PIPE] = {};
+    double host_t[4] = {};           // last ss_step_host: action check, copy+enqueue, waiting on the device, unpacking (seconds)
     float* ts_base = nullptr; double* ts_ctx = nullptr;      // create_temp_states scratch
 };
 
@@ -930,9 +941,8 @@ void ss_destroy(ss_env* E) {
     DevState& S = E->S;
     cudaFree(E->dm); cudaFree(S.pos); cudaFree(S.sv); cudaFree(S.warm); cudaFree(S.terrain); cudaFree(S.plank);
     cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.dbg);
-    cudaFreeHost(E->h_act); cudaFreeHost(E->h_obs); cudaFreeHost(E->h_rew); cudaFreeHost(E->h_epret);
-    cudaFreeHost(E->h_done); cudaFreeHost(E->h_to); cudaFreeHost(E->h_eplen);
-    cudaFree(E->d_act); cudaFree(E->d_obs); cudaFree(E->d_rew); cudaFree(E->d_epret); cudaFree(E->d_done); cudaFree(E->d_to); cudaFree(E->d_eplen);
+    cudaFreeHost(E->h_act); cudaFreeHost(E->h_rec); cudaFree(E->d_act); cudaFree(E->d_rec);
+    for (int k = 0; k < SS_PIPE; k++) if (E->pipe[k]) cudaStreamDestroy(E->pipe[k]);
     cudaFree(E->ts_base); cudaFree(E->ts_ctx);
     if (E->own) cudaStreamDestroy(E->own);
     delete E;
@@ -948,8 +958,10 @@ int ss_reset_all(ss_env* E, float* obs_dev, void* stream) {
 }
 
 static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el,
-                       cudaStream_t st, int physics) {
-    env_step_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics);
+                       cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr) {
+    if (e_end < 0) e_end = E->n;
+    env_step_kernel<<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
+                                                                       e_begin, e_end, packed);
     E->launches++;
     CK(cudaGetLastError());
     return SS_OK;
@@ -972,32 +984,60 @@ int ss_env_post(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev,
 static int ensure_staging(ss_env* E) {
     if (E->h_act) return SS_OK;
     size_t N = (size_t)E->n;
-    CK(cudaMallocHost(&E->h_act, N * NJ * 4)); CK(cudaMallocHost(&E->h_obs, N * SS_OBS * 4));
-    CK(cudaMallocHost(&E->h_rew, N * 4)); CK(cudaMallocHost(&E->h_epret, N * 4));
-    CK(cudaMallocHost(&E->h_done, N)); CK(cudaMallocHost(&E->h_to, N)); CK(cudaMallocHost(&E->h_eplen, N * 4));
-    CK(cudaMalloc(&E->d_act, N * NJ * 4)); CK(cudaMalloc(&E->d_obs, N * SS_OBS * 4));
-    CK(cudaMalloc(&E->d_rew, N * 4)); CK(cudaMalloc(&E->d_epret, N * 4));
-    CK(cudaMalloc(&E->d_done, N)); CK(cudaMalloc(&E->d_to, N)); CK(cudaMalloc(&E->d_eplen, N * 4));
+    CK(cudaMallocHost(&E->h_act, N * NJ * 4)); CK(cudaMallocHost(&E->h_rec, N * SS_REC * 4));
+    CK(cudaMalloc(&E->d_act, N * NJ * 4)); CK(cudaMalloc(&E->d_rec, N * SS_REC * 4));
+    for (int k = 0; k < SS_PIPE; k++) CK(cudaStreamCreateWithFlags(&E->pipe[k], cudaStreamNonBlocking));
     return SS_OK;
 }
 
-int ss_step_host(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el) {
+/* Host buffers in, host buffers out.  The batch is cut into up to SS_PIPE slices, each on its own stream: actions H2D ->
+ * env_step_kernel on the slice -> ONE D2H of the slice's packed result records; while the GPU works on the later
+ * slices the host unpacks the earlier ones into the caller's arrays, so only the last slice's copy-out is exposed. */
+int ss_step_host(ss_env* E, const float* act, float* obs, double* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el) {
     if (!E || !act || !obs || !rew || !done || !to || !er || !el) return fail(SS_ERR_ARG, "ss_step_host: null buffer");
     CK(cudaSetDevice(E->device));
     int rc = ensure_staging(E); if (rc) return rc;
-    size_t N = (size_t)E->n; cudaStream_t st = E->own;
-    memcpy(E->h_act, act, N * NJ * 4);
-    CK(cudaMemcpyAsync(E->d_act, E->h_act, N * NJ * 4, cudaMemcpyHostToDevice, st));
-    rc = launch_step(E, E->d_act, E->d_obs, E->d_rew, E->d_done, E->d_to, E->d_epret, E->d_eplen, st, 1); if (rc) return rc;
-    CK(cudaMemcpyAsync(E->h_obs, E->d_obs, N * SS_OBS * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(E->h_rew, E->d_rew, N * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(E->h_done, E->d_done, N, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(E->h_to, E->d_to, N, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(E->h_epret, E->d_epret, N * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(E->h_eplen, E->d_eplen, N * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    memcpy(obs, E->h_obs, N * SS_OBS * 4); memcpy(rew, E->h_rew, N * 4); memcpy(done, E->h_done, N);
-    memcpy(to, E->h_to, N); memcpy(er, E->h_epret, N * 4); memcpy(el, E->h_eplen, N * 4);
+    const int N = E->n;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now(), t_wait = 0, t_unpack = 0;
+    // robots.py:290 `assert np.isfinite(a).all()`: checked before anything is launched (read-only pass, then each slice
+    // is copied into the pinned buffer right before its H2D so that the GPU starts on slice 0 early)
+    {
+        const size_t cnt = (size_t)N * NJ;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(act);
+        uint32_t bad = 0;
+        for (size_t i = 0; i < cnt; i++) bad |= (uint32_t)((src[i] & 0x7f800000u) == 0x7f800000u);
+        if (bad) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
+    }
+    double t1 = now();
+    const int nslice = N >= 4096 ? SS_PIPE : (N >= 1024 ? 2 : 1);
+    int b[SS_PIPE + 1];
+    for (int k = 0; k <= nslice; k++) b[k] = (int)((int64_t)N * k / nslice / WARPS_PER_BLOCK) * WARPS_PER_BLOCK;
+    b[nslice] = N;
+    for (int k = 0; k < nslice; k++) {
+        cudaStream_t st = E->pipe[k];
+        const size_t n = (size_t)(b[k + 1] - b[k]);
+        memcpy(E->h_act + (size_t)b[k] * NJ, act + (size_t)b[k] * NJ, n * NJ * 4);
+        CK(cudaMemcpyAsync(E->d_act + (size_t)b[k] * NJ, E->h_act + (size_t)b[k] * NJ, n * NJ * 4, cudaMemcpyHostToDevice, st));
+        rc = launch_step(E, E->d_act, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, 1, b[k], b[k + 1], E->d_rec); if (rc) return rc;
+        CK(cudaMemcpyAsync(E->h_rec + (size_t)b[k] * SS_REC, E->d_rec + (size_t)b[k] * SS_REC, n * SS_REC * 4, cudaMemcpyDeviceToHost, st));
+    }
+    E->launches -= nslice - 1;          // one logical kernel launch per step (bench.py's gpu_launches counts steps)
+    double t2 = now();
+    for (int k = 0; k < nslice; k++) {
+        double ta = now();
+        CK(cudaStreamSynchronize(E->pipe[k]));
+        double tb = now(); t_wait += tb - ta;
+        for (int e = b[k]; e < b[k + 1]; e++) {
+            const float* r = E->h_rec + (size_t)e * SS_REC;
+            memcpy(obs + (size_t)e * SS_OBS, r, SS_OBS * 4);
+            int32_t len, flags; memcpy(&len, r + SS_OBS + 2, 4); memcpy(&flags, r + SS_OBS + 3, 4);
+            rew[e] = (double)r[SS_OBS]; er[e] = r[SS_OBS + 1]; el[e] = len;
+            done[e] = (uint8_t)(flags & 1); to[e] = (uint8_t)((flags >> 8) & 1);
+        }
+        t_unpack += now() - tb;
+    }
+    E->host_t[0] = t1 - t0; E->host_t[1] = t2 - t1; E->host_t[2] = t_wait; E->host_t[3] = t_unpack;
     return SS_OK;
 }
 
@@ -1005,10 +1045,12 @@ int ss_reset_host(ss_env* E, float* obs) {
     if (!E || !obs) return fail(SS_ERR_ARG, "ss_reset_host: null buffer");
     CK(cudaSetDevice(E->device));
     int rc = ensure_staging(E); if (rc) return rc;
-    rc = ss_reset_all(E, E->d_obs, E->own); if (rc) return rc;
-    CK(cudaMemcpyAsync(E->h_obs, E->d_obs, (size_t)E->n * SS_OBS * 4, cudaMemcpyDeviceToHost, E->own));
+    const size_t N = (size_t)E->n;
+    // d_rec doubles as the [N,60] observation buffer of the reset
+    rc = ss_reset_all(E, E->d_rec, E->own); if (rc) return rc;
+    CK(cudaMemcpyAsync(E->h_rec, E->d_rec, N * SS_OBS * 4, cudaMemcpyDeviceToHost, E->own));
     CK(cudaStreamSynchronize(E->own));
-    memcpy(obs, E->h_obs, (size_t)E->n * SS_OBS * 4);
+    memcpy(obs, E->h_rec, N * SS_OBS * 4);
     return SS_OK;
 }
 
@@ -1186,6 +1228,13 @@ int ss_gae(const float* rewards, const float* values, const float* masks, const 
     if (!rewards || !values || !masks || !bad_masks || !returns || T <= 0 || N <= 0) return fail(SS_ERR_ARG, "ss_gae: bad argument");
     gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, masks, bad_masks, returns, T, N, gamma, lam);
     CK(cudaGetLastError());
+    return SS_OK;
+}
+
+/* seconds the last ss_step_host spent copying+checking actions, enqueueing, waiting on the device, unpacking */
+int ss_host_timing(const ss_env* E, double* out4) {
+    if (!E || !out4) return fail(SS_ERR_ARG, "ss_host_timing: bad argument");
+    for (int i = 0; i < 4; i++) out4[i] = E->host_t[i];
     return SS_OK;
 }
 

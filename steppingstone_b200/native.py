@@ -87,6 +87,7 @@ _SIGNATURES = {
     "ss_debug_floats": (_I32, []),
     "ss_enable_debug": (ctypes.c_int, [_P, _I32]),
     "ss_debug_read": (ctypes.c_int, [_P, _P]),
+    "ss_host_timing": (ctypes.c_int, [_P, _P]),
     "ss_num_envs": (_I32, [_P]),
     "ss_launch_count": (ctypes.c_int64, [_P]),
     "ss_last_error": (ctypes.c_char_p, []),

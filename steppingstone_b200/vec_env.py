@@ -89,9 +89,6 @@ class BatchedStepperEnv:
         self.curriculum = 0
         N = self.num_envs
         if output == "numpy":
-            self._obs = np.zeros((N, OBS_DIM), np.float32)
-            self._rew = np.zeros(N, np.float32)
-            self._done = np.zeros(N, np.uint8)
             self._timeout = np.zeros(N, np.uint8)
             self._ep_ret = np.zeros(N, np.float32)
             self._ep_len = np.zeros(N, np.int32)
@@ -114,8 +111,9 @@ class BatchedStepperEnv:
     def reset(self):
         """ShmemVecEnv.reset (envs_utils.py:542-548)."""
         if self.output == "numpy":
-            native.check(self._lib.ss_reset_host(self._h, self._obs.ctypes.data), "ss_reset_host")
-            return self._obs.copy()
+            obs = np.empty((self.num_envs, OBS_DIM), np.float32)
+            native.check(self._lib.ss_reset_host(self._h, obs.ctypes.data), "ss_reset_host")
+            return obs
         native.check(self._lib.ss_reset_all(self._h, self._obs.data_ptr(), self._stream()), "ss_reset_all")
         return self._obs
 
@@ -128,20 +126,27 @@ class BatchedStepperEnv:
         if self.output == "numpy":
             a = np.ascontiguousarray(actions, dtype=np.float32)
             assert a.shape == (self.num_envs, ACT_DIM)
-            assert np.isfinite(a).all()                                         # robots.py:290
-            native.check(self._lib.ss_step_host(self._h, a.ctypes.data, self._obs.ctypes.data, self._rew.ctypes.data,
-                                                self._done.ctypes.data, self._timeout.ctypes.data,
-                                                self._ep_ret.ctypes.data, self._ep_len.ctypes.data), "ss_step_host")
-            dones = self._done.astype(bool)
-            t = round(time.time() - self._t0, 6)
+            N = self.num_envs
+            # fresh arrays every step, as ShmemVecEnv._decode_obses / step_wait return (envs_utils.py:556-558, 608-620)
+            obs = np.empty((N, OBS_DIM), np.float32); rew = np.empty(N, np.float64); dones = np.empty(N, np.bool_)
+            rc = self._lib.ss_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, dones.ctypes.data,
+                                        self._timeout.ctypes.data, self._ep_ret.ctypes.data, self._ep_len.ctypes.data)
+            if rc != 0:
+                assert np.isfinite(a).all()                                     # robots.py:290
+                native.check(rc, "ss_step_host")
             # one shared empty dict for the envs that did not finish (train.py:446-454 only reads keys)
-            infos = [_NO_INFO] * self.num_envs
-            for i in np.nonzero(dones)[0]:
-                infos[i] = {}
-                infos[i]["episode"] = {"r": round(float(self._ep_ret[i]), 6), "l": int(self._ep_len[i]), "t": t}
-                if self._timeout[i]:
-                    infos[i]["bad_transition"] = True
-            return self._obs.copy(), self._rew.astype(np.float64), dones, tuple(infos)
+            infos = [_NO_INFO] * N
+            idx = np.flatnonzero(dones)
+            if idx.size:                                                        # Monitor.update, envs_utils.py:136-151
+                t = round(time.time() - self._t0, 6)
+                rs = np.round(self._ep_ret[idx].astype(np.float64), 6).tolist()
+                ls = self._ep_len[idx].tolist(); tos = self._timeout[idx].tolist()
+                for i, r, l, to in zip(idx.tolist(), rs, ls, tos):
+                    info = {"episode": {"r": r, "l": l, "t": t}}
+                    if to:
+                        info["bad_transition"] = True                           # TimeLimitMask, envs_utils.py:62-63
+                    infos[i] = info
+            return obs, rew, dones, tuple(infos)
         torch = self._torch
         a = actions
         if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()):

@@ -443,3 +443,34 @@ def test_set_env_and_robot_params():
     a = random_actions(np.random.RandomState(2), n)
     g1.step(a); g2.step(0.5 * a)
     assert _maxerr(g1.substep_trace()[0], g2.substep_trace()[0]) < 1e-6
+
+
+def test_host_pipeline_matches_device_mode():
+    """ss_step_host cuts large batches into slices on separate streams (packed result records, unpacked on the host while
+    later slices run): bit-identical to the single-launch device path, ragged last slice included; a non-finite action
+    is refused before anything runs (robots.py:290)."""
+    import torch
+    n = 4100 + 7
+    gh = make_gpu_env(1, n); gd = make_gpu_env(1, n, output="torch")
+    gh.update_curriculum(5); gd.update_curriculum(5)
+    assert np.array_equal(gh.reset(), gd.reset().cpu().numpy())
+    rng = np.random.RandomState(11)
+    seen_done = 0
+    for t in range(45):
+        a = random_actions(rng, n, sd=0.6)
+        oh, rh, dh, ih = gh.step(a)
+        od, rd, dd, idv = gd.step(torch.tensor(a, device="cuda"))
+        assert oh.dtype == np.float32 and rh.dtype == np.float64 and dh.dtype == np.bool_ and len(ih) == n
+        assert np.array_equal(oh, od.cpu().numpy())
+        assert np.array_equal(rh.astype(np.float32), rd.cpu().numpy())
+        assert np.array_equal(dh, dd.cpu().numpy().astype(bool))
+        for i in np.flatnonzero(dh)[:5]:
+            assert ih[i]["episode"]["l"] == int(idv.episode_l[i]) and abs(ih[i]["episode"]["r"] - float(idv.episode_r[i])) < 1e-5
+        seen_done += int(dh.sum())
+    assert seen_done > 0
+    before = gh.get_state()
+    a[5, 3] = np.nan
+    with pytest.raises(AssertionError):
+        gh.step(a)
+    after = gh.get_state()
+    assert np.array_equal(before["q"], after["q"]) and np.array_equal(before["ints"], after["ints"])

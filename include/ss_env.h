@@ -28,7 +28,7 @@ extern "C" {
 #define SS_ERR_CUDA (-2)
 #define SS_ERR_STATE (-3)
 
-#define SS_NWARM 32      /* warm-start cache slots: capsule*8 + (stone&3)*2 + endpoint            */
+#define SS_NWARM 16      /* warm-start cache: ids of the last substep's <= 8 contacts (-1 = none), then their normal impulses */
 #define SS_NSCAL 16      /* doubles per env in ss_state_view.scalars                              */
 #define SS_NINT 8        /* int32 per env in ss_state_view.ints                                   */
 #define SS_MT_WORDS 625  /* MT19937: 624 state words + position                                   */
@@ -46,7 +46,7 @@ enum { SS_I_NEXT_STEP = 0, SS_I_REACHED_COUNT, SS_I_MIRRORED, SS_I_ELAPSED, SS_I
 typedef struct ss_state_view {
     double* q;         /* [N,28] base xyz, base quat (x,y,z,w), 21 hinge angles                   */
     double* qd;        /* [N,27] base angular vel (world), base linear vel (world), 21 hinge rates */
-    double* warm;      /* [N,32] cached normal impulses (Bullet manifold warm starting)           */
+    double* warm;      /* [N,16] contact ids [0..8) + cached normal impulses [8..16) (manifold warm starting) */
     double* terrain;   /* [N,n_steps,6] terrain_info: x,y,z,phi,x_tilt,y_tilt                     */
     double* plank;     /* [N,rendered,6] pose each plank body was last given                      */
     double* scalars;   /* [N,SS_NSCAL]                                                            */

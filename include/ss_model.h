@@ -30,7 +30,9 @@ extern "C" {
 #define SS_NQ 28        /* base xyz + quat(xyzw) + 21 hinge angles         */
 #define SS_OBS 60       /* walker3d_envs.py:552-556                        */
 #define SS_ACT 21
-#define SS_NCOL 4       /* foot capsules that collide with stones          */
+#define SS_NCOL 4       /* foot capsules (geoms 0..3 of the geom table)    */
+#define SS_NGEOM 22     /* collision geoms: capsules and spheres (W3D 22, Mike 20) */
+#define SS_MAX_PAIRS 160 /* self-collision geom pairs (W3D 141, Mike 100)  */
 #define SS_MAX_STONES 100 /* rendered_step_count upper bound (W3D 100)     */
 #define SS_MAX_CONTACTS 8 /* contact points kept per env per substep       */
 #define SS_MAX_LIMIT_ROWS 8
@@ -64,6 +66,17 @@ typedef struct ss_model {
     double init_q[SS_NJ];      /* "running_start", robots.py:535-545                      */
     double init_pos[3];        /* walker3d_envs.py:823 / mike.py:344                      */
     double total_mass;
+    /* Every collision geom of the MJCF (walker3d.xml:17-97): a capsule [p0,p1] or a sphere (p0 == p1) of `radius` in the
+     * frame of body geom_body.  Geoms 0..3 are the foot capsules (= col_*).  geom_stone: the link's contype/conaffinity
+     * (the LAST geom of the link decides, as in Bullet's MJCF importer) passes the static stones' filter
+     * (group StaticFilter, mask AllFilter ^ StaticFilter) -- torso, waist and butt do not.  geom_breaking = 0.02 x the
+     * angular-motion disc of the link's compound shape (manifold breaking threshold).  pair_a/pair_b: geom pairs that
+     * can self-collide under URDF_USE_SELF_COLLISION | URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS (robots.py:496-500):
+     * different links, neither an ancestor of the other, (group_a & mask_b) && (group_b & mask_a). */
+    int32_t n_geom, n_pair;
+    int32_t geom_body[SS_NGEOM], geom_foot[SS_NGEOM] /* -1, 0 right, 1 left */, geom_stone[SS_NGEOM], geom_sphere[SS_NGEOM];
+    double geom_radius[SS_NGEOM], geom_p0[SS_NGEOM][3], geom_p1[SS_NGEOM][3], geom_breaking[SS_NGEOM];
+    int32_t pair_a[SS_MAX_PAIRS], pair_b[SS_MAX_PAIRS];
 } ss_model;
 
 typedef struct ss_params {
@@ -95,7 +108,7 @@ typedef struct ss_params {
     int32_t n_phantoms;        /* 20 / 0: RNG draws only (walker3d_envs.py:566-580)       */
     int32_t use_sampler;       /* Mike 1 (mike.py:593), W3D 0 (walker3d_envs.py:1083)     */
     int32_t actuator_mode;     /* 0 torque held over the step (robots.py:289-293), 1 PD   */
-    int32_t reserved0;
+    int32_t collision_mode;    /* 0 feet vs stones only, 1 every link vs stones, 2 + self-collision (reference) */
     double done_height;        /* 0.7                                                     */
     double electricity_cost, stall_torque_cost, joints_at_limit_cost;
     double step_radius;        /* 0.25                                                    */
@@ -105,6 +118,13 @@ typedef struct ss_params {
     double control_dt;         /* 1/60 (scene.dt)                                         */
     double yaw_samples[SS_GRID], pitch_samples[SS_GRID], r_samples[SS_GRID];
     double xtilt_samples[SS_GRID], ytilt_samples[SS_GRID];
+    /* link-link contacts of the robot with itself: hard contacts (no stiffness/damping on the robot's links) */
+    double self_friction;      /* 1.2 * 1.2 (walker3d.xml:5, both links)                  */
+    double self_erp;           /* setDefaultContactERP(0.9), bullet_utils.py:324          */
+    double stone_breaking;     /* 0.02 x angular-motion disc of the plank's compound      */
+    int32_t self_cross_terms;  /* 0: Bullet's row denominator J_a H^-1 J_a^T + J_b H^-1 J_b^T (no cross terms when both
+                                  sides are the same multibody); 1: the exact (J_a-J_b) H^-1 (J_a-J_b)^T */
+    int32_t reserved1;
 } ss_params;
 
 #ifdef __cplusplus

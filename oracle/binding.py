@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libss_oracle.so")
 
-NQ, ND, NJ, OBS, NWARM, NSCAL, NINT, MTW = 28, 27, 21, 60, 32, 16, 8, 625
+NQ, ND, NJ, OBS, NWARM, NSCAL, NINT, MTW = 28, 27, 21, 60, 16, 16, 8, 625
 
 
 class StateView(ctypes.Structure):
@@ -176,7 +176,7 @@ class Oracle:
         return dict(mass=out[0], com=out[1:4].copy(), P=out[4:7].copy(), L=out[7:10].copy(), ke=out[10], pe=out[11])
 
     def contacts(self, i=0):
-        out = np.zeros((NWARM, 8))
+        out = np.zeros((8, 16))
         assert self.lib.sso_contacts(self.h, i, _ptr(out)) == 0
         return out
 

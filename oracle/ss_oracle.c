@@ -357,9 +357,13 @@ static void contact_jacobian(const ss_model* M, const kin_t* K, int body, const 
 }
 
 /* ------------------------------------------------------------------------------------------------
- * collision: foot capsules vs the planks around next_step_index
+ * collision.  Stone candidates: (geom, plank slot, segment end) -> id geom*8 + slot*2 + end, for every geom whose
+ * link passes the stones' collision filter (collision_mode 0: the foot capsules only).  Self-collision candidates
+ * (collision_mode 2): one closest-point pair per geom pair of M->pair_a/b -> id SS_NGEOM*8 + pair.  The SS_MAX_CONTACTS
+ * deepest candidates (ties by id) become contacts, ordered by id.
  * ---------------------------------------------------------------------------------------------- */
-typedef struct { int active; int body; double depth, n[3], x[3]; } cand_t;
+typedef struct { int active, id, body, body_b; double depth, n[3], x[3], xb[3]; } cand_t;
+#define MAXCAND (SS_NGEOM * 8 + SS_MAX_PAIRS)
 
 static void plank_box(const ss_params* P, const double* pl, double* Rs, double* cb) {
     /* bullet_objects.py:75-80 + plank.urdf: the body is placed by its COM frame (q12) */
@@ -369,75 +373,136 @@ static void plank_box(const ss_params* P, const double* pl, double* Rs, double* 
     cb[0] = pl[0] + t[0]; cb[1] = pl[1] + t[1]; cb[2] = pl[2] - P->stone_com_z + t[2];
 }
 
-static void detect(const ss_model* M, const ss_params* P, const env_t* e, const kin_t* K, cand_t* cand) {
-    for (int l = 0; l < SS_NWARM; l++) {
-        cand_t* c = &cand[l];
-        c->active = 0; c->depth = 0; c->n[0] = c->n[1] = c->n[2] = 0; c->x[0] = c->x[1] = c->x[2] = 0;
-        int cap = l >> 3, slot = (l >> 1) & 3, end = l & 1;
+/* capsule segment [p0,p1] (world) of radius r against the plank box (Rs, cb): end 0 / 1 of the part of the segment
+ * above the plank's footprint; returns 0 if this end yields no candidate */
+static int capsule_box(const ss_params* P, const double* Rs, const double* cb, const double* w0, const double* w1, double r,
+                       int end, double breaking, cand_t* c) {
+    double p0[3], p1[3], a[3], bb[3];
+    for (int i = 0; i < 3; i++) { p0[i] = w0[i] - cb[i]; p1[i] = w1[i] - cb[i]; }
+    m3tv(Rs, p0, a); m3tv(Rs, p1, bb);
+    /* clip the segment to the plank's footprint (local x,y slabs); keep the full segment if it misses */
+    double t0 = 0, t1 = 1; int empty = 0;
+    for (int ax = 0; ax < 2; ax++) {
+        double d = bb[ax] - a[ax], h = P->stone_half[ax];
+        if (fabs(d) < 1e-12) { if (fabs(a[ax]) > h) empty = 1; }
+        else {
+            double ta = (-h - a[ax]) / d, tb = (h - a[ax]) / d;
+            if (ta > tb) { double s = ta; ta = tb; tb = s; }
+            if (ta > t0) t0 = ta;
+            if (tb < t1) t1 = tb;
+        }
+    }
+    if (empty || t0 > t1) { t0 = 0; t1 = 1; }
+    if (end == 1 && t1 - t0 < 1e-6) return 0;
+    double tt = end ? t1 : t0, s[3], q[3], nl[3], dist;
+    for (int i = 0; i < 3; i++) s[i] = a[i] + tt * (bb[i] - a[i]);
+    int inside = 1;
+    for (int i = 0; i < 3; i++) {
+        double h = P->stone_half[i];
+        q[i] = s[i] < -h ? -h : (s[i] > h ? h : s[i]);
+        if (q[i] != s[i]) inside = 0;
+    }
+    if (!inside) {
+        double d[3] = { s[0] - q[0], s[1] - q[1], s[2] - q[2] };
+        dist = sqrt(dot3(d, d));
+        for (int i = 0; i < 3; i++) nl[i] = d[i] / dist;
+    } else {
+        int ax = 0; double best = 1e30;
+        for (int i = 0; i < 3; i++) { double m = P->stone_half[i] - fabs(s[i]); if (m < best) { best = m; ax = i; } }
+        nl[0] = nl[1] = nl[2] = 0; nl[ax] = s[ax] >= 0 ? 1.0 : -1.0;
+        dist = -best;
+    }
+    c->depth = dist - r;
+    if (!(c->depth < breaking)) return 0;
+    m3v(Rs, nl, c->n);
+    double sw[3]; m3v(Rs, s, sw);
+    for (int i = 0; i < 3; i++) { c->x[i] = sw[i] + cb[i] - r * c->n[i]; c->xb[i] = c->x[i]; }
+    return 1;
+}
+
+/* closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9) */
+static void segment_segment(const double* p1, const double* q1, const double* p2, const double* q2, double* c1, double* c2) {
+    double d1[3], d2[3], r[3];
+    for (int i = 0; i < 3; i++) { d1[i] = q1[i] - p1[i]; d2[i] = q2[i] - p2[i]; r[i] = p1[i] - p2[i]; }
+    double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), s, t;
+    const double EPS = 1e-12;
+    if (a <= EPS && e <= EPS) { s = t = 0; }
+    else if (a <= EPS) { s = 0; t = f / e; t = t < 0 ? 0 : (t > 1 ? 1 : t); }
+    else {
+        double c = dot3(d1, r);
+        if (e <= EPS) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+        else {
+            double b = dot3(d1, d2), denom = a * e - b * b;
+            if (denom > EPS * a * e) { s = (b * f - c * e) / denom; s = s < 0 ? 0 : (s > 1 ? 1 : s); } else s = 0;
+            t = (b * s + f) / e;
+            if (t < 0) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+            else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+        }
+    }
+    for (int i = 0; i < 3; i++) { c1[i] = p1[i] + d1[i] * s; c2[i] = p2[i] + d2[i] * t; }
+}
+
+/* returns the number of contacts written to out[] (<= SS_MAX_CONTACTS, ordered by id) */
+static int detect(const ss_model* M, const ss_params* P, const env_t* e, const kin_t* K, cand_t* out) {
+    static _Thread_local cand_t cand[MAXCAND];
+    int n = 0;
+    double gw0[SS_NGEOM][3], gw1[SS_NGEOM][3];
+    for (int g = 0; g < M->n_geom; g++) {
+        int b = M->geom_body[g]; double t[3];
+        m3v(K->Rw[b], M->geom_p0[g], t); for (int i = 0; i < 3; i++) gw0[g][i] = K->ow[b][i] + t[i];
+        m3v(K->Rw[b], M->geom_p1[g], t); for (int i = 0; i < 3; i++) gw1[g][i] = K->ow[b][i] + t[i];
+    }
+    for (int slot = 0; slot < 4; slot++) {
         int k = -1;
         for (int kk = e->next_step - 2; kk <= e->next_step + 1; kk++) if (kk >= 0 && (kk & 3) == slot) k = kk;
         if (k < 0 || k > P->n_steps - 1) continue;
-        const double* pl = e->plank + 6 * (k % P->rendered);
         double Rs[9], cb[3];
-        plank_box(P, pl, Rs, cb);
-        int b = M->col_body[cap];
-        c->body = b;
-        double p0[3], p1[3], a[3], bb[3], t[3];
-        m3v(K->Rw[b], M->col_p0[cap], t); for (int i = 0; i < 3; i++) p0[i] = K->ow[b][i] + t[i] - cb[i];
-        m3v(K->Rw[b], M->col_p1[cap], t); for (int i = 0; i < 3; i++) p1[i] = K->ow[b][i] + t[i] - cb[i];
-        m3tv(Rs, p0, a); m3tv(Rs, p1, bb);
-        /* clip the segment to the plank's footprint (local x,y slabs); keep the full segment if it misses */
-        double t0 = 0, t1 = 1; int empty = 0;
-        for (int ax = 0; ax < 2; ax++) {
-            double d = bb[ax] - a[ax], h = P->stone_half[ax];
-            if (fabs(d) < 1e-12) { if (fabs(a[ax]) > h) empty = 1; }
-            else {
-                double ta = (-h - a[ax]) / d, tb = (h - a[ax]) / d;
-                if (ta > tb) { double s = ta; ta = tb; tb = s; }
-                if (ta > t0) t0 = ta;
-                if (tb < t1) t1 = tb;
+        plank_box(P, e->plank + 6 * (k % P->rendered), Rs, cb);
+        for (int g = 0; g < M->n_geom; g++) {
+            if (!M->geom_stone[g] || (P->collision_mode == 0 && M->geom_foot[g] < 0)) continue;
+            double breaking = M->geom_breaking[g] < P->stone_breaking ? M->geom_breaking[g] : P->stone_breaking;
+            for (int end = 0; end < (M->geom_sphere[g] ? 1 : 2); end++) {
+                cand_t c; memset(&c, 0, sizeof c);
+                if (!capsule_box(P, Rs, cb, gw0[g], gw1[g], M->geom_radius[g], end, breaking, &c)) continue;
+                c.active = 1; c.id = g * 8 + slot * 2 + end; c.body = M->geom_body[g]; c.body_b = -1;
+                cand[n++] = c;
             }
         }
-        if (empty || t0 > t1) { t0 = 0; t1 = 1; }
-        if (end == 1 && t1 - t0 < 1e-6) continue;
-        double tt = end ? t1 : t0, s[3], q[3], nl[3], dist;
-        for (int i = 0; i < 3; i++) s[i] = a[i] + tt * (bb[i] - a[i]);
-        int inside = 1;
-        for (int i = 0; i < 3; i++) {
-            double h = P->stone_half[i];
-            q[i] = s[i] < -h ? -h : (s[i] > h ? h : s[i]);
-            if (q[i] != s[i]) inside = 0;
-        }
-        if (!inside) {
-            double d[3] = { s[0] - q[0], s[1] - q[1], s[2] - q[2] };
-            dist = sqrt(dot3(d, d));
-            for (int i = 0; i < 3; i++) nl[i] = d[i] / dist;
-        } else {
-            int ax = 0; double best = 1e30;
-            for (int i = 0; i < 3; i++) { double m = P->stone_half[i] - fabs(s[i]); if (m < best) { best = m; ax = i; } }
-            nl[0] = nl[1] = nl[2] = 0; nl[ax] = s[ax] >= 0 ? 1.0 : -1.0;
-            dist = -best;
-        }
-        double r = M->col_radius[cap];
-        c->depth = dist - r;
-        if (!(c->depth < M->contact_breaking)) continue;
-        c->active = 1;
-        m3v(Rs, nl, c->n);
-        double sw[3]; m3v(Rs, s, sw);
-        for (int i = 0; i < 3; i++) c->x[i] = sw[i] + cb[i] - r * c->n[i];
     }
-    /* keep the SS_MAX_CONTACTS deepest (ties by slot) */
-    int nact = 0; for (int l = 0; l < SS_NWARM; l++) nact += cand[l].active;
-    if (nact > MAXC) {
-        int keep[SS_NWARM];
-        for (int l = 0; l < SS_NWARM; l++) {
-            int rank = 0;
-            for (int m = 0; m < SS_NWARM; m++)
-                if (cand[m].active && (cand[m].depth < cand[l].depth || (cand[m].depth == cand[l].depth && m < l))) rank++;
-            keep[l] = cand[l].active && rank < MAXC;
+    if (P->collision_mode >= 2)
+        for (int p = 0; p < M->n_pair; p++) {
+            int ga = M->pair_a[p], gb = M->pair_b[p];
+            double ca[3], cb2[3], d[3];
+            segment_segment(gw0[ga], gw1[ga], gw0[gb], gw1[gb], ca, cb2);
+            for (int i = 0; i < 3; i++) d[i] = ca[i] - cb2[i];
+            double dist = sqrt(dot3(d, d)), ra = M->geom_radius[ga], rb = M->geom_radius[gb];
+            double breaking = M->geom_breaking[ga] < M->geom_breaking[gb] ? M->geom_breaking[ga] : M->geom_breaking[gb];
+            if (!(dist - ra - rb < breaking)) continue;
+            cand_t c; memset(&c, 0, sizeof c);
+            c.active = 1; c.id = SS_NGEOM * 8 + p; c.body = M->geom_body[ga]; c.body_b = M->geom_body[gb];
+            c.depth = dist - ra - rb;
+            if (dist > 1e-9) for (int i = 0; i < 3; i++) c.n[i] = d[i] / dist; else { c.n[0] = c.n[1] = 0; c.n[2] = 1; }
+            for (int i = 0; i < 3; i++) { c.x[i] = ca[i] - ra * c.n[i]; c.xb[i] = cb2[i] + rb * c.n[i]; }
+            cand[n++] = c;
         }
-        for (int l = 0; l < SS_NWARM; l++) cand[l].active = keep[l];
+    /* keep the SS_MAX_CONTACTS deepest (ties by id); candidates are already in id order within each class and the
+     * stone ids (< SS_NGEOM*8) precede the pair ids, but the stone loop runs slot-major: sort the survivors by id */
+    int m = 0;
+    for (int l = 0; l < n; l++) {
+        int rank = 0;
+        for (int q = 0; q < n; q++)
+            if (cand[q].depth < cand[l].depth || (cand[q].depth == cand[l].depth && cand[q].id < cand[l].id)) rank++;
+        if (rank < MAXC) out[m++] = cand[l];
     }
+    for (int i = 1; i < m; i++) { cand_t c = out[i]; int j = i - 1; while (j >= 0 && out[j].id > c.id) { out[j + 1] = out[j]; j--; } out[j + 1] = c; }
+    return m;
+}
+
+/* does a contact touch foot f (right 0 / left 1)?  calc_feet_state counts contacts with ANY body, self-collisions
+ * included */
+static int contact_on_foot(const ss_model* M, const cand_t* c, int f) {
+    int fb = M->foot_body[f];
+    return c->body == fb || c->body_b == fb;
 }
 
 /* btPlaneSpace1 */
@@ -483,12 +548,12 @@ static void integrate(const ss_params* P, env_t* e) {
 }
 
 static void substep(const ss_model* M, const ss_params* P, env_t* e, const double* tau) {
-    kin_t K; aba_t A; cand_t cand[SS_NWARM];
+    kin_t K; aba_t A; cand_t con[MAXC];
     double h = P->dt;
     fk(M, e, &K);
-    detect(M, P, e, &K, cand);                       /* collision detection at the current pose */
+    int nc = detect(M, P, e, &K, con);               /* collision detection at the current pose */
     e->cache_contact[0] = e->cache_contact[1] = 0;
-    for (int l = 0; l < SS_NWARM; l++) if (cand[l].active) e->cache_contact[M->col_foot[l >> 3]] = 1;
+    for (int c = 0; c < nc; c++) for (int f = 0; f < 2; f++) if (contact_on_foot(M, &con[c], f)) e->cache_contact[f] = 1;
     aba_prepare(M, &K, &A);
     double acc[ND], gv[ND];
     forward_dynamics(M, &K, &A, e, tau, P->gravity, acc);
@@ -497,7 +562,7 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
     clamp_vel(P, gv);
 
     /* ---- constraint rows: violated hinge limits, then contact normals, then 2 friction rows each ---- */
-    row_t rows[MAXR]; int nl = 0, nc = 0, slot_of[MAXC];
+    row_t rows[MAXR]; int nl = 0;
     for (int j = 0; j < NJ && nl < MAXL; j++) {
         for (int side = 0; side < 2 && nl < MAXL; side++) {
             double pen = side ? M->q_hi[j] - e->qj[j] : e->qj[j] - M->q_lo[j];
@@ -513,11 +578,14 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
             r->cfm = 0; r->lo = 0; r->hi = P->limit_max_impulse; r->normal = -1;
         }
     }
-    for (int l = 0; l < SS_NWARM; l++) if (cand[l].active) slot_of[nc++] = l;
+    /* stones are soft (contactStiffness / contactDamping, bullet_objects.py:61-69); link-link contacts are hard:
+     * erp = the default contact ERP (bullet_utils.py:324), cfm = 0 */
     double kd = h * P->contact_stiffness + P->contact_damping;
-    double cfm = 1.0 / kd / h, erp = h * P->contact_stiffness / kd;
+    double cfm_stone = 1.0 / kd / h, erp_stone = h * P->contact_stiffness / kd;
     for (int c = 0; c < nc; c++) {
-        cand_t* cd = &cand[slot_of[c]];
+        cand_t* cd = &con[c];
+        int self = cd->body_b >= 0;
+        double cfm = self ? 0.0 : cfm_stone, erp = self ? P->self_erp : erp_stone, mu = self ? P->self_friction : P->friction;
         double t1[3], t2[3]; plane_space(cd->n, t1, t2);
         const double* dirs[3] = { cd->n, t1, t2 };
         for (int a = 0; a < 3; a++) {
@@ -525,7 +593,22 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
             memset(r, 0, sizeof *r);
             contact_jacobian(M, &K, cd->body, cd->x, dirs[a], r->J);
             unit_response(M, &K, &A, -1, 0, cd->body, cd->x, dirs[a], r->W);
-            double d = 0, rel = 0; for (int k = 0; k < ND; k++) { d += r->J[k] * r->W[k]; rel += r->J[k] * gv[k]; }
+            double d = 0; for (int k = 0; k < ND; k++) d += r->J[k] * r->W[k];
+            if (self) {
+                /* body B of the same multibody gets the opposite impulse at its own surface point */
+                double Jb[ND], Wb[ND];
+                contact_jacobian(M, &K, cd->body_b, cd->xb, dirs[a], Jb);
+                unit_response(M, &K, &A, -1, 0, cd->body_b, cd->xb, dirs[a], Wb);
+                if (P->self_cross_terms) {
+                    d = 0; for (int k = 0; k < ND; k++) d += (r->J[k] - Jb[k]) * (r->W[k] - Wb[k]);
+                } else {
+                    /* btMultiBodyConstraintSolver::setupMultiBodyContactConstraint: denom0 (A) + denom1 (B), each side
+                     * on its own -- no cross terms even when A and B are links of one multibody */
+                    for (int k = 0; k < ND; k++) d += Jb[k] * Wb[k];
+                }
+                for (int k = 0; k < ND; k++) { r->J[k] -= Jb[k]; r->W[k] -= Wb[k]; }
+            }
+            double rel = 0; for (int k = 0; k < ND; k++) rel += r->J[k] * gv[k];
             r->invD = 1.0 / (d + cfm);
             r->cfm = cfm * r->invD;
             if (a == 0) {
@@ -533,10 +616,10 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
                 if (pen > 0) velerr -= pen / h; else poserr = -pen * erp / h;
                 r->rhs = (poserr + velerr) * r->invD;
                 r->lo = 0; r->hi = 1e10; r->normal = -1;
-                r->lam = e->warm[slot_of[c]] * P->warmstart;
+                for (int w = 0; w < MAXC; w++) if ((int)e->warm[w] == cd->id) r->lam = e->warm[MAXC + w] * P->warmstart;
             } else {
                 r->rhs = -rel * r->invD;
-                r->mu = P->friction; r->normal = nl + c;
+                r->mu = mu; r->normal = nl + c;
             }
         }
     }
@@ -566,8 +649,8 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
         for (int k = 0; k < ND; k++) gv[k] += dv[k];
         clamp_vel(P, gv);
     }
-    memset(e->warm, 0, sizeof e->warm);
-    for (int c = 0; c < nc; c++) e->warm[slot_of[c]] = rows[nl + c].lam;
+    for (int w = 0; w < MAXC; w++) { e->warm[w] = -1; e->warm[MAXC + w] = 0; }
+    for (int c = 0; c < nc; c++) { e->warm[c] = con[c].id; e->warm[MAXC + c] = rows[nl + c].lam; }
     unpack_vel(e, gv);
     integrate(P, e);
 }
@@ -820,7 +903,8 @@ static void env_reset(const struct sso_env* S, env_t* e, float* obs) {
      * w = v = 0 after every reset. */
     e->v[0] = e->v[1] = e->v[2] = 0;
     e->w[0] = e->w[1] = e->w[2] = 0;
-    for (int l = 0; l < SS_NWARM; l++) if (!isfinite(e->warm[l])) e->warm[l] = 0;   /* the cache survives resets (q4); a NaN must not */
+    for (int l = 0; l < MAXC; l++)                       /* the cache survives resets (q4); a NaN must not */
+        if (!isfinite(e->warm[l]) || !isfinite(e->warm[MAXC + l])) { e->warm[l] = -1; e->warm[MAXC + l] = 0; }
     /* WalkerBase.reset robots.py:433-439 */
     e->feet_contact[0] = e->feet_contact[1] = 0;
     memset(e->feet_xyz, 0, sizeof e->feet_xyz);
@@ -902,6 +986,7 @@ int sso_create(const ss_model* model, const ss_params* params, int32_t n, const 
         memcpy(e->rng.mt, mt_env + (size_t)i * SS_MT_WORDS, 624 * 4); e->rng.pos = mt_env[(size_t)i * SS_MT_WORDS + 624];
         if (mt_aux) { memcpy(e->grng.mt, mt_aux + (size_t)i * SS_MT_WORDS, 624 * 4); e->grng.pos = mt_aux[(size_t)i * SS_MT_WORDS + 624]; }
         e->quat[3] = 1;
+        for (int w = 0; w < MAXC; w++) e->warm[w] = -1;
         memcpy(e->pos, model->init_pos, 24);
         memcpy(e->qj, model->init_q, sizeof e->qj);
     }
@@ -1185,12 +1270,14 @@ int sso_invariants(sso_env* S, const double* q, const double* qd, double* out) {
 }
 
 int sso_contacts(sso_env* S, int32_t i, double* out) {
-    kin_t K; cand_t cand[SS_NWARM];
+    kin_t K; cand_t con[MAXC];
     fk(&S->M, &S->e[i], &K);
-    detect(&S->M, &S->P, &S->e[i], &K, cand);
-    for (int l = 0; l < SS_NWARM; l++) {
-        double* o = out + 8 * l;
-        o[0] = cand[l].active; o[1] = cand[l].depth; memcpy(o + 2, cand[l].n, 24); memcpy(o + 5, cand[l].x, 24);
+    int nc = detect(&S->M, &S->P, &S->e[i], &K, con);
+    memset(out, 0, sizeof(double) * MAXC * 16);
+    for (int c = 0; c < nc; c++) {
+        double* o = out + 16 * c;
+        o[0] = 1; o[1] = con[c].depth; memcpy(o + 2, con[c].n, 24); memcpy(o + 5, con[c].x, 24);
+        o[8] = con[c].id; o[9] = con[c].body; o[10] = con[c].body_b; memcpy(o + 11, con[c].xb, 24);
     }
     return 0;
 }

@@ -36,8 +36,13 @@ constexpr int MAXC = SS_MAX_CONTACTS, MAXL = SS_MAX_LIMIT_ROWS;
 struct alignas(16) DevModel {
     float anchor[NB][3]; float R0[NB][9]; float axis[NB][3]; float mass[NB]; float com[NB][3]; float inertia[NB][6];
     float q_lo[NJ], q_hi[NJ], tau_max[NJ], damping[NJ], pd_p[NJ], pd_d[NJ], init_q[NJ];
-    float col_p0[SS_NCOL][3], col_p1[SS_NCOL][3], col_radius[SS_NCOL];
-    int col_body[SS_NCOL], col_foot[SS_NCOL];
+    // collision geoms (capsule / sphere per body), stone candidate table (geom | slot << 5 | end << 7), self-collision pairs
+    float geom_p0[SS_NGEOM][3], geom_p1[SS_NGEOM][3], geom_radius[SS_NGEOM], geom_half[SS_NGEOM], geom_breaking[SS_NGEOM];
+    unsigned char geom_body[SS_NGEOM + 2];
+    unsigned char pair_a[SS_MAX_PAIRS], pair_b[SS_MAX_PAIRS];
+    unsigned short scand[SS_NGEOM * 8];
+    int n_geom, n_pair, n_scand, collision_mode, self_cross_terms, pad2;
+    float stone_breaking, self_friction, self_erp, stone_radius;
     int foot_body[2]; float foot_ref[2][3];
     int anc_mask[NB];
     float contact_breaking, gravity, dt, erp_limit, cfm_contact, erp_contact, friction, linear_slop, warmstart,
@@ -72,12 +77,14 @@ constexpr int DBG_H = 0, DBG_C = 729, DBG_CAND = 756, DBG_ROWS = 756 + 256, DBG_
 // per-warp scratch
 struct alignas(16) WarpSmem {
     float S[NB][6];
-    float foot[2][12];
+    float pose[NB][12];       // body poses of this substep: R (9, to world axes), origin rel. the base origin (3)
+    float gw[SS_NGEOM][8];    // geom segments in the common frame: p0 (3), p1 (3), radius, pad
     float stone[4][16];       // per candidate slot: box centre rel. step-start base pos (3), R (9), valid, pad
     float vec[64];            // v* (27) / obs staging (60)
-    float con[MAXC][12];      // n3, x3, depth, body, slot
+    float con[MAXC][16];      // n3, point on A 3, depth, body A, candidate id, warm impulse, point on B 3, body B (-1 stone)
     float lim[MAXL][4];       // hinge, dir, penetration
     float dinv[32];
+    double parked[4];         // base position (fp64) parked during the substeps
     union {
         struct { float H[HS * HS]; float Z[32 * ZS]; } s;
         double d[(HS * HS + 32 * ZS) / 2];
@@ -89,7 +96,7 @@ static_assert(sizeof(((WarpSmem*)0)->u.d) >= 7 * SS_MAX_STONES * sizeof(double),
 // scratch of the dynamics-only kernel (aba_substep): same member names, no constraint-solver storage
 struct alignas(16) WarpSmemDyn {
     float S[NB][6];
-    float foot[2][12];
+    float pose[NB][12];
     float dinv[32];
     struct { struct { float H[HS * HS]; } s; } u;
 };
@@ -238,9 +245,9 @@ __device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int la
 //   in : quat[4] (all lanes), q_dof, v_dof (lane = dof: 0..2 base angular, 3..5 base linear, 6.. hinges),
 //        tau_dof (hinge torque for lanes 6..26, else 0)
 //   out: acc (lane = dof);  W.u.s.H holds L (unit lower, row stride HS), W.dinv holds 1/D
-//        W.S holds the hinge motion vectors, W.foot the foot body poses
+//        W.S holds the hinge motion vectors, W.pose the body poses
 // ---------------------------------------------------------------------------------------------
-template <typename WS>
+template <bool DIAG, typename WS>
 __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const float* quat, float q_dof, float v_dof,
                                                float tau_dof, int lane, float* dbg) {
     const int ss = seg_start(lane), se = seg_end(lane);
@@ -253,14 +260,12 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
 #pragma unroll
         for (int i = 0; i < 6; i++) W.S[lane][i] = S[i];
     }
+    if (isb) {
 #pragma unroll
-    for (int f = 0; f < 2; f++)
-        if (lane == M.foot_body[f]) {
+        for (int i = 0; i < 9; i++) W.pose[lane][i] = X.R[i];
 #pragma unroll
-            for (int i = 0; i < 9; i++) W.foot[f][i] = X.R[i];
-#pragma unroll
-            for (int i = 0; i < 3; i++) W.foot[f][9 + i] = X.p[i];
-        }
+        for (int i = 0; i < 3; i++) W.pose[lane][9 + i] = X.p[i];
+    }
     // rigid-body inertia about the common origin: m, h = m c, Ibar (xx yy zz xy xz yz)
     float m = 0, h[3] = { 0, 0, 0 }, I[6] = { 0, 0, 0, 0, 0, 0 };
     if (isb) {
@@ -402,7 +407,7 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
 #pragma unroll
         for (int j = 0; j < ND; j++) if (lane >= ND && j == lane) Hr[j] = 1.f;
     }
-    if (dbg) {
+    if (DIAG && dbg) {
         if (lane < ND) {
 #pragma unroll
             for (int j = 0; j < ND; j++) dbg[DBG_H + lane * ND + j] = Hr[j];
@@ -473,103 +478,305 @@ __device__ __forceinline__ void integrate_warp(const DevModel& M, float* quat, f
 }
 
 // ---------------------------------------------------------------------------------------------
+// collision detection.  Candidates are evaluated 32 at a time (lane = candidate):
+//   stone passes  (geom, plank slot, segment end) from M.scand -- feet first, then limbs, then spheres; id geom*8+slot*2+end
+//   pair passes   one closest-point pair per self-collision geom pair (collision_mode 2); id SS_NGEOM*8 + pair
+// and merged into a pool of the MAXC deepest (ties by id) kept in W.con.  The pool is finally ordered by id and the cached
+// normal impulse of each contact is looked up in the previous substep's list (`warm`: lanes 0..7 ids, 8..15 impulses).
+// Passes whose candidates are all out of reach (bounding test) are skipped.  Returns the number of contacts.
+// ---------------------------------------------------------------------------------------------
+struct Cand { bool active; float depth; int id; float n[3], x[3], xb[3]; int ba, bb; };
+
+__device__ __forceinline__ void con_write(float* c, const Cand& k) {
+    c[0] = k.n[0]; c[1] = k.n[1]; c[2] = k.n[2]; c[3] = k.x[0]; c[4] = k.x[1]; c[5] = k.x[2];
+    c[6] = k.depth; c[7] = (float)k.ba; c[8] = (float)k.id; c[9] = 0.f;
+    c[10] = k.xb[0]; c[11] = k.xb[1]; c[12] = k.xb[2]; c[13] = (float)k.bb;
+}
+
+__device__ __noinline__ int pool_merge_slow(WarpSmem* Wp, int npool, bool active, float depth, int id, const float* rec, int lane) {
+    // more than MAXC candidates: keep the MAXC deepest of (pool U new), ties by id
+    WarpSmem& W = *Wp;
+    const unsigned amask = __ballot_sync(FULL, active);
+    float pd = 1e30f; int pid = 0x7fffffff;
+    if (lane < npool) { pd = W.con[lane][6]; pid = (int)W.con[lane][8]; }
+    int rank_new = 0, rank_pool = 0;
+    for (int m = 0; m < 32; m++) {
+        float od = shfl(depth, m); int oid = shfl(id, m);
+        if ((amask >> m) & 1) {
+            if (od < depth || (od == depth && oid < id)) rank_new++;
+            if (od < pd || (od == pd && oid < pid)) rank_pool++;
+        }
+    }
+    for (int k = 0; k < npool; k++) {
+        float od = shfl(pd, k); int oid = shfl(pid, k);
+        if (od < depth || (od == depth && oid < id)) rank_new++;
+        if (od < pd || (od == pd && oid < pid)) rank_pool++;
+    }
+    const bool keep_new = active && rank_new < MAXC, keep_pool = lane < npool && rank_pool < MAXC;
+    const unsigned pm = __ballot_sync(FULL, keep_pool), nm = __ballot_sync(FULL, keep_new);
+    const unsigned lt = (1u << lane) - 1u;
+    float tmp[16];
+    if (keep_pool) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) tmp[i] = W.con[lane][i];
+    }
+    __syncwarp();
+    if (keep_pool) {
+        float* c = W.con[__popc(pm & lt)];
+#pragma unroll
+        for (int i = 0; i < 16; i++) c[i] = tmp[i];
+    }
+    if (keep_new) {
+        float* c = W.con[__popc(pm) + __popc(nm & lt)];
+#pragma unroll
+        for (int i = 0; i < 16; i++) c[i] = rec[i];
+    }
+    __syncwarp();
+    return __popc(pm) + __popc(nm);
+}
+
+__device__ __forceinline__ void pool_add(WarpSmem& W, int& npool, const Cand& k, int lane) {
+    const unsigned amask = __ballot_sync(FULL, k.active);
+    const int na = __popc(amask);
+    if (na == 0) return;
+    if (npool + na <= MAXC) {
+        if (k.active) con_write(W.con[npool + __popc(amask & ((1u << lane) - 1u))], k);
+        npool += na;
+        __syncwarp();
+        return;
+    }
+    float rec[16];
+    con_write(rec, k); rec[14] = rec[15] = 0.f;
+    npool = pool_merge_slow(&W, npool, k.active, k.depth, k.id, rec, lane);
+}
+
+// capsule segment (a -> b, plank-local coordinates) of radius r against the plank box: one end of the part of the segment
+// above the plank's footprint
+__device__ __forceinline__ void stone_candidate(const DevModel& M, const float* st, const float* g, int endp, float breaking,
+                                                const float* dpos, Cand& k) {
+    float p0[3], p1[3], a[3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { p0[i] = g[i] + dpos[i] - st[i]; p1[i] = g[3 + i] + dpos[i] - st[i]; }
+    matTvec3(st + 3, p0, a); matTvec3(st + 3, p1, b);
+    float t0 = 0.f, t1 = 1.f; bool empty = false;
+#pragma unroll
+    for (int ax = 0; ax < 2; ax++) {
+        float d = b[ax] - a[ax], hh = M.stone_half[ax];
+        if (fabsf(d) < 1e-12f) { if (fabsf(a[ax]) > hh) empty = true; }
+        else {
+            float ta = (-hh - a[ax]) / d, tb = (hh - a[ax]) / d;
+            if (ta > tb) { float s = ta; ta = tb; tb = s; }
+            t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+        }
+    }
+    if (empty || t0 > t1) { t0 = 0.f; t1 = 1.f; }
+    if (endp == 1 && t1 - t0 < 1e-6f) return;
+    float tt = endp ? t1 : t0, s[3], q[3], nl[3], dist;
+    bool inside = true;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        s[i] = a[i] + tt * (b[i] - a[i]);
+        float hh = M.stone_half[i];
+        q[i] = fminf(fmaxf(s[i], -hh), hh);
+        if (q[i] != s[i]) inside = false;
+    }
+    if (!inside) {
+        float d[3] = { s[0] - q[0], s[1] - q[1], s[2] - q[2] };
+        dist = sqrtf(dot3(d, d));
+        float inv = 1.f / dist;
+        nl[0] = d[0] * inv; nl[1] = d[1] * inv; nl[2] = d[2] * inv;
+    } else {
+        int ax = 0; float best = 1e30f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { float mm = M.stone_half[i] - fabsf(s[i]); if (mm < best) { best = mm; ax = i; } }
+        nl[0] = nl[1] = nl[2] = 0.f;
+        float sg = (ax == 0 ? s[0] : (ax == 1 ? s[1] : s[2])) >= 0.f ? 1.f : -1.f;
+        if (ax == 0) nl[0] = sg; else if (ax == 1) nl[1] = sg; else nl[2] = sg;
+        dist = -best;
+    }
+    const float r = g[6];
+    k.depth = dist - r;
+    if (k.depth < breaking) {
+        k.active = true;
+        matvec3(st + 3, nl, k.n);
+        float sw[3]; matvec3(st + 3, s, sw);
+        // contact point on the robot, relative to the CURRENT base origin
+#pragma unroll
+        for (int i = 0; i < 3; i++) { k.x[i] = sw[i] + st[i] - dpos[i] - r * k.n[i]; k.xb[i] = k.x[i]; }
+    }
+}
+
+// closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9), as the oracle's segment_segment
+__device__ __forceinline__ void segment_segment(const float* p1, const float* q1, const float* p2, const float* q2, float* c1, float* c2) {
+    float d1[3], d2[3], r[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { d1[i] = q1[i] - p1[i]; d2[i] = q2[i] - p2[i]; r[i] = p1[i] - p2[i]; }
+    const float a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r);
+    const float EPS = 1e-12f;
+    float s, t;
+    auto clamp01 = [](float x) { return fminf(fmaxf(x, 0.f), 1.f); };
+    if (a <= EPS && e <= EPS) { s = t = 0.f; }
+    else if (a <= EPS) { s = 0.f; t = clamp01(f / e); }
+    else {
+        const float c = dot3(d1, r);
+        if (e <= EPS) { t = 0.f; s = clamp01(-c / a); }
+        else {
+            const float b = dot3(d1, d2), denom = a * e - b * b;
+            s = denom > EPS * a * e ? clamp01((b * f - c * e) / denom) : 0.f;
+            t = (b * s + f) / e;
+            if (t < 0.f) { t = 0.f; s = clamp01(-c / a); }
+            else if (t > 1.f) { t = 1.f; s = clamp01((b - c) / a); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { c1[i] = p1[i] + d1[i] * s; c2[i] = p2[i] + d2[i] * t; }
+}
+
+__device__ __forceinline__ int collide_warp(const DevModel& M, WarpSmem& W, const float* dpos, float warm, int lane, int& cflags) {
+    // geom segments in the common frame
+    if (lane < M.n_geom) {
+        const float* P = W.pose[M.geom_body[lane]];
+        float t0[3], t1[3];
+        matvec3(P, M.geom_p0[lane], t0); matvec3(P, M.geom_p1[lane], t1);
+        float* g = W.gw[lane];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { g[i] = P[9 + i] + t0[i]; g[3 + i] = P[9 + i] + t1[i]; }
+        g[6] = M.geom_radius[lane]; g[7] = 0.f;
+    }
+    __syncwarp();
+    int npool = 0;
+    // ---- stones ----
+    for (int base = 0; base < M.n_scand; base += 32) {
+        Cand k; k.active = false; k.depth = 0.f; k.id = 0; k.ba = 0; k.bb = -1;
+        const int ci = base + lane;
+        bool near = false;
+        int g = 0, slot = 0, endp = 0;
+        if (ci < M.n_scand) {
+            const int code = M.scand[ci];
+            g = code & 31; slot = (code >> 5) & 3; endp = (code >> 7) & 1;
+            const float* st = W.stone[slot];
+            if (st[12] != 0.f) {
+                // bounding test: distance of the segment midpoint to the plank box vs half length + radius
+                const float* gg = W.gw[g];
+                float d[3], dl[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) d[i] = 0.5f * (gg[i] + gg[3 + i]) + dpos[i] - st[i];
+                matTvec3(st + 3, d, dl);
+#pragma unroll
+                for (int i = 0; i < 3; i++) dl[i] = fmaxf(fabsf(dl[i]) - M.stone_half[i], 0.f);
+                float reach = M.geom_half[g] + gg[6] + M.stone_breaking + 1e-4f;
+                near = dot3(dl, dl) < reach * reach;
+            }
+        }
+        if (base > 0 && !__any_sync(FULL, near)) continue;
+        if (near) {
+            stone_candidate(M, W.stone[slot], W.gw[g], endp, fminf(M.geom_breaking[g], M.stone_breaking), dpos, k);
+            k.id = g * 8 + slot * 2 + endp; k.ba = M.geom_body[g];
+        }
+        pool_add(W, npool, k, lane);
+    }
+    // ---- the robot against itself ----
+    if (M.collision_mode >= 2) {
+        for (int base = 0; base < M.n_pair; base += 32) {
+            Cand k; k.active = false; k.depth = 0.f; k.id = 0; k.ba = 0; k.bb = -1;
+            const int pi = base + lane;
+            bool near = false;
+            int ga = 0, gb = 0;
+            if (pi < M.n_pair) {
+                ga = M.pair_a[pi]; gb = M.pair_b[pi];
+                const float *A = W.gw[ga], *B = W.gw[gb];
+                float d[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) d[i] = 0.5f * ((A[i] + A[3 + i]) - (B[i] + B[3 + i]));
+                float reach = M.geom_half[ga] + A[6] + M.geom_half[gb] + B[6] + 0.01f;
+                near = dot3(d, d) < reach * reach;
+            }
+            if (!__any_sync(FULL, near)) continue;
+            if (near) {
+                const float *A = W.gw[ga], *B = W.gw[gb];
+                float ca[3], cb[3], d[3];
+                segment_segment(A, A + 3, B, B + 3, ca, cb);
+#pragma unroll
+                for (int i = 0; i < 3; i++) d[i] = ca[i] - cb[i];
+                const float dist = sqrtf(dot3(d, d)), ra = A[6], rb = B[6];
+                k.depth = dist - ra - rb;
+                if (k.depth < fminf(M.geom_breaking[ga], M.geom_breaking[gb])) {
+                    k.active = true;
+                    if (dist > 1e-9f) { float inv = 1.f / dist; k.n[0] = d[0] * inv; k.n[1] = d[1] * inv; k.n[2] = d[2] * inv; }
+                    else { k.n[0] = k.n[1] = 0.f; k.n[2] = 1.f; }
+#pragma unroll
+                    for (int i = 0; i < 3; i++) { k.x[i] = ca[i] - ra * k.n[i]; k.xb[i] = cb[i] + rb * k.n[i]; }
+                    k.id = SS_NGEOM * 8 + pi; k.ba = M.geom_body[ga]; k.bb = M.geom_body[gb];
+                }
+            }
+            pool_add(W, npool, k, lane);
+        }
+    }
+    cflags = 0;
+    if (npool == 0) return 0;
+    // ---- order by id, look the cached impulses up, foot flags ----
+    {
+        float rec[16]; int myid = 0x7fffffff;
+        if (lane < npool) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) rec[i] = W.con[lane][i];
+            myid = (int)rec[8];
+        }
+        int rank = 0; float lam0 = 0.f;
+        for (int j = 0; j < npool; j++) { int oid = shfl(myid, j); if (oid < myid) rank++; }
+#pragma unroll
+        for (int w = 0; w < MAXC; w++) {
+            float wid = shfl(warm, w), wl = shfl(warm, MAXC + w);
+            if ((int)wid == myid) lam0 = wl;
+        }
+        __syncwarp();
+        bool f0 = false, f1 = false;
+        if (lane < npool) {
+            rec[9] = lam0;
+            float* c = W.con[rank];
+#pragma unroll
+            for (int i = 0; i < 14; i++) c[i] = rec[i];
+            const int ba = (int)rec[7], bb = (int)rec[13];
+            f0 = ba == M.foot_body[0] || bb == M.foot_body[0];
+            f1 = ba == M.foot_body[1] || bb == M.foot_body[1];
+        }
+        if (__any_sync(FULL, f0)) cflags |= 1;
+        if (__any_sync(FULL, f1)) cflags |= 2;
+        __syncwarp();
+    }
+    return npool;
+}
+
+// ---------------------------------------------------------------------------------------------
 // one physics substep.  State in registers: quat (all lanes), q_dof / v_dof (lane = dof), dpos =
 // displacement of the base since the start of the control step (all lanes), warm (lane = candidate slot).
 // Returns the per-foot contact flags of this substep's collision pass (bit f).
 // ---------------------------------------------------------------------------------------------
+template <bool DIAG>
 __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, float* quat, float& q_dof, float& v_dof,
                                             float tau_dof, float* dpos, float& warm, int lane, float* dbg) {
     const float hdt = M.dt;
-    float acc = dynamics_warp(M, W, quat, q_dof, v_dof, tau_dof, lane, dbg);
+    float acc = dynamics_warp<DIAG>(M, W, quat, q_dof, v_dof, tau_dof, lane, dbg);
     float vs = v_dof + hdt * acc;
     vs = fminf(fmaxf(vs, -M.max_coord_vel), M.max_coord_vel);
     if (lane >= ND) vs = 0.f;
 
-    // ---- collision: lane = (capsule, plank slot, segment end) ----
-    bool active = false; float depth = 0.f, cn[3] = { 0, 0, 0 }, cx[3] = { 0, 0, 0 };
-    const int cap = lane >> 3, slot = (lane >> 1) & 3, endp = lane & 1;
-    const int cbody = M.col_body[cap];
-    {
-        const float* st = W.stone[slot];
-        if (st[12] != 0.f) {
-            const float* fp = W.foot[M.col_foot[cap]];
-            float p0[3], p1[3], a[3], b[3], t[3];
-            matvec3(fp, M.col_p0[cap], t);
-#pragma unroll
-            for (int i = 0; i < 3; i++) p0[i] = fp[9 + i] + t[i] + dpos[i] - st[i];
-            matvec3(fp, M.col_p1[cap], t);
-#pragma unroll
-            for (int i = 0; i < 3; i++) p1[i] = fp[9 + i] + t[i] + dpos[i] - st[i];
-            matTvec3(st + 3, p0, a); matTvec3(st + 3, p1, b);
-            float t0 = 0.f, t1 = 1.f; bool empty = false;
-#pragma unroll
-            for (int ax = 0; ax < 2; ax++) {
-                float d = b[ax] - a[ax], hh = M.stone_half[ax];
-                if (fabsf(d) < 1e-12f) { if (fabsf(a[ax]) > hh) empty = true; }
-                else {
-                    float ta = (-hh - a[ax]) / d, tb = (hh - a[ax]) / d;
-                    if (ta > tb) { float s = ta; ta = tb; tb = s; }
-                    t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
-                }
-            }
-            if (empty || t0 > t1) { t0 = 0.f; t1 = 1.f; }
-            if (!(endp == 1 && t1 - t0 < 1e-6f)) {
-                float tt = endp ? t1 : t0, s[3], q[3], nl[3], dist;
-                bool inside = true;
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    s[i] = a[i] + tt * (b[i] - a[i]);
-                    float hh = M.stone_half[i];
-                    q[i] = fminf(fmaxf(s[i], -hh), hh);
-                    if (q[i] != s[i]) inside = false;
-                }
-                if (!inside) {
-                    float d[3] = { s[0] - q[0], s[1] - q[1], s[2] - q[2] };
-                    dist = sqrtf(dot3(d, d));
-                    float inv = 1.f / dist;
-                    nl[0] = d[0] * inv; nl[1] = d[1] * inv; nl[2] = d[2] * inv;
-                } else {
-                    int ax = 0; float best = 1e30f;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) { float mm = M.stone_half[i] - fabsf(s[i]); if (mm < best) { best = mm; ax = i; } }
-                    nl[0] = nl[1] = nl[2] = 0.f;
-                    float sg = (ax == 0 ? s[0] : (ax == 1 ? s[1] : s[2])) >= 0.f ? 1.f : -1.f;
-                    if (ax == 0) nl[0] = sg; else if (ax == 1) nl[1] = sg; else nl[2] = sg;
-                    dist = -best;
-                }
-                float r = M.col_radius[cap];
-                depth = dist - r;
-                if (depth < M.contact_breaking) {
-                    active = true;
-                    matvec3(st + 3, nl, cn);
-                    float sw[3]; matvec3(st + 3, s, sw);
-                    // contact point on the robot, relative to the CURRENT base origin
-#pragma unroll
-                    for (int i = 0; i < 3; i++) cx[i] = sw[i] + st[i] - dpos[i] - r * cn[i];
-                }
-            }
-        }
-    }
-    unsigned amask = __ballot_sync(FULL, active);
-    if (__popc(amask) > MAXC) {          // keep the deepest MAXC (ties by slot)
-        int rank = 0;
-        for (int mlane = 0; mlane < 32; mlane++) {
-            float od = shfl(depth, mlane);
-            bool oa = (amask >> mlane) & 1;
-            if (oa && (od < depth || (od == depth && mlane < lane))) rank++;
-        }
-        active = active && rank < MAXC;
-        amask = __ballot_sync(FULL, active);
-    }
-    const int nc = __popc(amask);
-    const int cidx = __popc(amask & ((1u << lane) - 1u));
+    // ---- collision (see collide_warp): <= MAXC contacts in W.con, ordered by candidate id, warm impulses looked up ----
     int cflags = 0;
-    if (amask & 0x0000ffffu) cflags |= 1 << M.col_foot[0];
-    if (amask & 0xffff0000u) cflags |= 1 << M.col_foot[2];
-    if (dbg) {
+    const int nc = collide_warp(M, W, dpos, warm, lane, cflags);
+    bool anyself = false;
+    if (lane < nc) anyself = W.con[lane][13] >= 0.f;
+    anyself = __any_sync(FULL, anyself);
+    if (DIAG && dbg) {
         float* d = dbg + DBG_CAND + lane * 8;
-        d[0] = active ? 1.f : 0.f; d[1] = depth; d[2] = cn[0]; d[3] = cn[1]; d[4] = cn[2];
-        d[5] = cx[0]; d[6] = cx[1]; d[7] = cx[2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) d[i] = 0.f;
+        __syncwarp();
+        if (lane < nc) {
+            const float* c = W.con[lane]; float* o = dbg + DBG_CAND + lane * 16;
+            o[0] = 1.f; o[1] = c[6]; o[2] = c[0]; o[3] = c[1]; o[4] = c[2]; o[5] = c[3]; o[6] = c[4]; o[7] = c[5];
+            o[8] = c[8]; o[9] = c[7]; o[10] = c[13]; o[11] = c[10]; o[12] = c[11]; o[13] = c[12];
+        }
     }
 
     // ---- violated hinge limits (lane = dof) ----
@@ -584,52 +791,69 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
     const int nr = nl + 3 * nc;
 
     float dv = 0.f;          // constraint velocity change (lane = dof)
-    float newwarm = 0.f;
+    float newwarm = lane < MAXC ? -1.f : 0.f;
 #if SS_SYNC >= 2
     __syncthreads();         // phase alignment: row build
 #endif
     if (nr > 0) {
         // publish row definitions
         if (lviol && lidx < MAXL) { W.lim[lidx][0] = (float)(lane - 6); W.lim[lidx][1] = lviol == 1 ? 1.f : -1.f; W.lim[lidx][2] = lpen; }
-        if (active) {
-            float* c = W.con[cidx];
-            c[0] = cn[0]; c[1] = cn[1]; c[2] = cn[2]; c[3] = cx[0]; c[4] = cx[1]; c[5] = cx[2];
-            c[6] = depth; c[7] = (float)cbody; c[8] = (float)lane; c[9] = warm;
-        }
         if (lane < ND) W.vec[lane] = vs;
         __syncwarp();
 
         // ---- lane = row slot: Jacobian row, z = L^-1 J^T ----
         // Fixed slots (compile-time row indices in the solver): 0..7 contact normals, 8..23 friction (two per contact,
         // contact-major as Bullet orders them), 24..31 violated hinge limits.  Inactive slots carry all-zero rows.
+        // A link-link contact acts on two bodies of the tree: J = J_a - J_b.  When the env has one (warp-uniform), rows
+        // go through the substitution twice (a side, b side): Bullet's row denominator is J_a H^-1 J_a^T + J_b H^-1 J_b^T
+        // (no cross terms), which needs both halves separately.
         const int r = lane;
         float z[HS];
-#pragma unroll
-        for (int k = 0; k < HS; k++) z[k] = 0.f;
         int rtype = -1;      // 0 limit, 1 normal, 2/3 friction
         int nidx = -1; float pen = 0.f, lam = 0.f;
+        int ccon = -1, hj = -1, maskA = 0, maskB = 0; bool selfrow = false;
+        float dir[3] = { 0.f, 0.f, 0.f }, xa[3] = { 0.f, 0.f, 0.f }, xb[3] = { 0.f, 0.f, 0.f }, ldir = 0.f;
         {
-            int c = -1, a = 0;
-            if (r < MAXC) { if (r < nc) c = r; }
-            else if (r < 3 * MAXC) { int cc = (r - MAXC) >> 1; if (cc < nc) { c = cc; a = 1 + ((r - MAXC) & 1); nidx = cc; } }
+            int a = 0;
+            if (r < MAXC) { if (r < nc) ccon = r; }
+            else if (r < 3 * MAXC) { int cc = (r - MAXC) >> 1; if (cc < nc) { ccon = cc; a = 1 + ((r - MAXC) & 1); nidx = cc; } }
             else if (r - 3 * MAXC < nl) {
                 rtype = 0;
                 const float* ld = W.lim[r - 3 * MAXC];
-                int hj = (int)ld[0]; float dir = ld[1]; pen = ld[2];
-#pragma unroll
-                for (int k = 6; k < ND; k++) z[k] = (k - 6 == hj) ? dir : 0.f;
+                hj = (int)ld[0]; ldir = ld[1]; pen = ld[2];
             }
-            if (c >= 0) {
+            if (ccon >= 0) {
                 rtype = 1 + a;
-                const float* cd = W.con[c];
-                float n[3] = { cd[0], cd[1], cd[2] }, x[3] = { cd[3], cd[4], cd[5] }, dir[3], t1[3], t2[3];
+                const float* cd = W.con[ccon];
+                float n[3] = { cd[0], cd[1], cd[2] }, t1[3], t2[3];
                 plane_space(n, t1, t2);
 #pragma unroll
-                for (int i = 0; i < 3; i++) dir[i] = a == 0 ? n[i] : (a == 1 ? t1[i] : t2[i]);
+                for (int i = 0; i < 3; i++) { dir[i] = a == 0 ? n[i] : (a == 1 ? t1[i] : t2[i]); xa[i] = cd[3 + i]; xb[i] = cd[10 + i]; }
                 pen = cd[6]; if (a == 0) lam = cd[9] * M.warmstart;
-                float wr[3]; cross3(x, dir, wr);
+                maskA = M.anc_mask[(int)cd[7]];
+                const int bodyB = (int)cd[13];
+                selfrow = bodyB >= 0;
+                if (selfrow) maskB = M.anc_mask[bodyB];
+            }
+        }
+        float rel = 0.f, dsides = 0.f;
+        const int npass = anyself ? 2 : 1;
+        float* Z = W.u.s.Z;
+#pragma unroll 1
+        for (int pass = 0; pass < npass; pass++) {
+#pragma unroll
+            for (int k = 0; k < HS; k++) z[k] = 0.f;
+            if (pass == 0 && rtype == 0) {
+#pragma unroll
+                for (int k = 6; k < ND; k++) z[k] = (k - 6 == hj) ? ldir : 0.f;
+            }
+            if (ccon >= 0 && (pass == 0 || selfrow)) {
+                float x[3], wr[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) x[i] = pass == 0 ? xa[i] : xb[i];
+                const int mask = pass == 0 ? maskA : maskB;
+                cross3(x, dir, wr);
                 z[0] = wr[0]; z[1] = wr[1]; z[2] = wr[2]; z[3] = dir[0]; z[4] = dir[1]; z[5] = dir[2];
-                int mask = M.anc_mask[(int)cd[7]];
 #pragma unroll
                 for (int i = 1; i < NB; i++) {
                     const float* Si = W.S[i];
@@ -637,28 +861,43 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                     z[5 + i] = ((mask >> i) & 1) ? v : 0.f;
                 }
             }
-        }
-        // relative velocity along the row before the solve: J v*
-        float rel = 0.f;
+            // relative velocity along the row before the solve: J v*
+            float relp = 0.f;
 #pragma unroll
-        for (int k = 0; k < ND; k++) rel += z[k] * W.vec[k];
-        // forward substitution with the unit lower factor, row by row (broadcast LDS.128 reads of L)
-        const float* L = W.u.s.H;
+            for (int k = 0; k < ND; k++) relp += z[k] * W.vec[k];
+            rel += pass == 0 ? relp : -relp;
+            // forward substitution with the unit lower factor, row by row (broadcast LDS.128 reads of L)
+            const float* L = W.u.s.H;
 #pragma unroll
-        for (int i = 1; i < ND; i++) {
-            const float4* Li = reinterpret_cast<const float4*>(L + i * HS);
-            float acc = z[i];
+            for (int i = 1; i < ND; i++) {
+                const float4* Li = reinterpret_cast<const float4*>(L + i * HS);
+                float acc = z[i];
 #pragma unroll
-            for (int j = 0; j < (i + 3) / 4; j++) {
-                float4 l = Li[j];
-                if (4 * j < i) acc = fmaf(-l.x, z[4 * j], acc);
-                if (4 * j + 1 < i) acc = fmaf(-l.y, z[4 * j + 1], acc);
-                if (4 * j + 2 < i) acc = fmaf(-l.z, z[4 * j + 2], acc);
-                if (4 * j + 3 < i) acc = fmaf(-l.w, z[4 * j + 3], acc);
+                for (int j = 0; j < (i + 3) / 4; j++) {
+                    float4 l = Li[j];
+                    if (4 * j < i) acc = fmaf(-l.x, z[4 * j], acc);
+                    if (4 * j + 1 < i) acc = fmaf(-l.y, z[4 * j + 1], acc);
+                    if (4 * j + 2 < i) acc = fmaf(-l.z, z[4 * j + 2], acc);
+                    if (4 * j + 3 < i) acc = fmaf(-l.w, z[4 * j + 3], acc);
+                }
+                z[i] = acc;
             }
-            z[i] = acc;
+            if (npass == 2) {
+#pragma unroll
+                for (int k = 0; k < ND; k++) dsides = fmaf(z[k] * W.dinv[k], z[k], dsides);
+                float4* Zr = reinterpret_cast<float4*>(Z + r * ZS);
+                if (pass == 0) {
+#pragma unroll
+                    for (int j = 0; j < ZS / 4; j++) Zr[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < ZS / 4; j++) {
+                        float4 v = Zr[j];
+                        z[4 * j] = v.x - z[4 * j]; z[4 * j + 1] = v.y - z[4 * j + 1]; z[4 * j + 2] = v.z - z[4 * j + 2]; z[4 * j + 3] = v.w - z[4 * j + 3];
+                    }
+                }
+            }
         }
-        float* Z = W.u.s.Z;
         {
             float4* Zr = reinterpret_cast<float4*>(Z + r * ZS);
 #pragma unroll
@@ -669,18 +908,21 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         float diag = 0.f;
 #pragma unroll
         for (int k = 0; k < ND; k++) { float w = z[k] * W.dinv[k]; diag = fmaf(w, z[k], diag); z[k] = w; }
-        // row constants (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint / btMultiBodyJointLimitConstraint)
+        // row constants (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint / btMultiBodyJointLimitConstraint).
+        // Stones are soft (contactStiffness / contactDamping -> cfm, erp); link-link contacts are hard (cfm 0, default contact ERP).
         float invD = 0.f, rhs = 0.f, cfmt = 0.f, lo = 0.f, hi = 0.f;
+        if (selfrow && !M.self_cross_terms) diag = dsides;
         if (rtype == 0) {
             invD = 1.f / diag;
             rhs = (-pen * M.erp_limit / hdt - rel) * invD;
             hi = M.limit_max_impulse;
         } else if (rtype >= 1) {
-            invD = 1.f / (diag + M.cfm_contact);
-            cfmt = M.cfm_contact * invD;
+            const float cfm = selfrow ? 0.f : M.cfm_contact, erp = selfrow ? M.self_erp : M.erp_contact;
+            invD = 1.f / (diag + cfm);
+            cfmt = cfm * invD;
             if (rtype == 1) {
                 float p = pen + M.linear_slop, poserr = 0.f, velerr = -rel;
-                if (p > 0.f) velerr -= p / hdt; else poserr = -p * M.erp_contact / hdt;
+                if (p > 0.f) velerr -= p / hdt; else poserr = -p * erp / hdt;
                 rhs = (poserr + velerr) * invD;
                 hi = 1e10f;
             } else rhs = -rel * invD;
@@ -729,7 +971,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
 #pragma unroll
             for (int j = 0; j < ZS / 4; j++) Zr[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
         }
-        if (dbg) {
+        if (DIAG && dbg) {
             dbg[DBG_ROWS + 0] = (float)nl; dbg[DBG_ROWS + 1] = (float)nc;
             float* d = dbg + DBG_ROWS + 4 + lane * 6;
             d[0] = (float)rtype; d[1] = invD; d[2] = rhs; d[3] = rel; d[4] = diag; d[5] = lam;
@@ -742,7 +984,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         //      normal block: one shuffle per iteration.
         const bool isfric = nidx >= 0;
         const int nsrc = isfric ? nidx : lane;
-        const float mu = M.friction;
+        const float mu = selfrow ? M.self_friction : M.friction;
         // friction rows start dead (bounds pinned to the current impulse => no change) until their normal pushes
         float lo_c = isfric ? lam : lo, hi_c = isfric ? lam : hi;
         float c = rhs;
@@ -782,7 +1024,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 }
         }
 #undef SS_ROW_STEP
-        if (dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
+        if (DIAG && dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
         // ---- velocity update: dv = L^-T sum_r w_r lam_r ----
         float u = 0.f;
         auto gather = [&](int s0, int s1) {
@@ -790,9 +1032,11 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         };
         gather(0, nc); gather(MAXC, MAXC + 2 * nc); gather(3 * MAXC, 3 * MAXC + nl);
         dv = solve_lt(W, u, lane);
-        // warm-start cache: candidate lane reads its normal row's impulse
-        float lw = shfl(lam, cidx & (MAXC - 1));
-        newwarm = active ? lw : 0.f;
+        // warm-start cache for the next substep: lanes 0..7 the contact ids, lanes 8..15 their normal impulses
+        float lw = shfl(lam, (lane - MAXC) & (MAXC - 1));
+        newwarm = -1.f;
+        if (lane < nc) newwarm = W.con[lane][8];
+        else if (lane >= MAXC) newwarm = (lane - MAXC < nc) ? lw : 0.f;
         __syncwarp();
     }
     warm = newwarm;

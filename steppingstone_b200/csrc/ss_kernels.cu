@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <string>
 #include <vector>
 #include <chrono>
@@ -91,7 +92,7 @@ __device__ __forceinline__ void env_load_phys(const DevState& S, int e, int lane
     E.q_dof = shfl(a, (lane + 30) & 31);            // hinge j sits at sv[4+j]; dof 6+j reads lane j+4
     if (lane < 6 || lane >= ND) E.q_dof = 0.f;
     E.v_dof = lane < ND ? b : 0.f;
-    E.warm = S.warm[(size_t)e * SS_NWARM + lane];
+    E.warm = lane < SS_NWARM ? S.warm[(size_t)e * SS_NWARM + lane] : 0.f;     // lanes 0..7 contact ids, 8..15 impulses
 #pragma unroll
     for (int i = 0; i < 3; i++) E.pos[i] = S.pos[(size_t)e * 3 + i];
     E.next_step = S.ints[(size_t)e * SS_NINT + SS_I_NEXT_STEP];
@@ -127,7 +128,7 @@ __device__ __forceinline__ void env_store(const DevState& S, int e, int lane, co
     else if (lane < 4 + NJ) a = qh;
     sv[lane] = a;
     sv[32 + lane] = lane < ND ? E.v_dof : 0.f;
-    S.warm[(size_t)e * SS_NWARM + lane] = E.warm;
+    if (lane < SS_NWARM) S.warm[(size_t)e * SS_NWARM + lane] = E.warm;
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 3; i++) S.pos[(size_t)e * 3 + i] = E.pos[i];
@@ -411,7 +412,10 @@ __device__ __forceinline__ void env_reset(const DevModel& M, const DevState& S, 
     float q = 0.f;
     if (j >= 0 && j < NJ) { q = M.init_q[src]; if (E.mirrored && (j == 0 || j == 2)) q = -q; }
     E.q_dof = q; E.v_dof = 0.f;           // resetBasePositionAndOrientation zeroes both base velocities (oracle env_reset)
-    if (!isfinite(E.warm)) E.warm = 0.f;  // the warm-start cache survives resets (q4); a NaN must not
+    {   // the warm-start cache survives resets (q4); a NaN must not
+        float other = shfl(E.warm, lane ^ SS_MAX_CONTACTS);
+        if (!isfinite(E.warm) || (lane < SS_NWARM && !isfinite(other))) E.warm = lane < SS_MAX_CONTACTS ? -1.f : 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < 3; i++) E.pos[i] = M.init_pos[i];
     E.quat[0] = E.quat[1] = E.quat[2] = 0.f; E.quat[3] = 1.f;
@@ -474,6 +478,9 @@ __device__ __forceinline__ void setup_stones(const DevModel& M, const DevState& 
 // ---------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// DIAG = per-substep trace / debug dump requested (parity tests): a second instantiation, so that the production kernel
+// carries neither the code nor the registers of the probes.
+template <bool DIAG>
 __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel* gm, DevState S, const float* __restrict__ act,
                                                          float* __restrict__ obs, float* __restrict__ rew,
                                                          uint8_t* __restrict__ done, uint8_t* __restrict__ timeout,
@@ -514,14 +521,17 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     int cflags = -1;
     if (physics) {
         setup_stones(M, S, W, e, E, lane);
+        // the double-precision base position is not needed inside the substeps (they integrate the displacement dpos):
+        // park it in shared memory so that it does not hold six registers through the solver
+        if (lane < 3) W.parked[lane] = E.pos[lane];
         float dpos[3] = { 0.f, 0.f, 0.f };
         for (int s = 0; s < M.n_substeps; s++) {
 #if SS_SYNC
             __syncthreads();                     // re-align the CTA's warps so that they share instruction fetches
 #endif
-            float* dbg = (S.dbg && s == M.n_substeps - 1) ? S.dbg + (size_t)e * DBG_FLOATS : nullptr;
-            cflags = substep_warp(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg);
-            if (S.trace_q && s < 4 && !ghost) {
+            float* dbg = (DIAG && S.dbg && s == M.n_substeps - 1) ? S.dbg + (size_t)e * DBG_FLOATS : nullptr;
+            cflags = substep_warp<DIAG>(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg);
+            if (DIAG && S.trace_q && s < 4 && !ghost) {
                 double* tq = S.trace_q + ((size_t)s * S.n + e) * SS_NQ;
                 double* tv = S.trace_qd + ((size_t)s * S.n + e) * ND;
                 if (lane < 3) tq[lane] = E.pos[lane] + (double)(lane == 0 ? dpos[0] : lane == 1 ? dpos[1] : dpos[2]);
@@ -530,8 +540,9 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
                 if (lane < ND) tv[lane] = E.v_dof;
             }
         }
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 3; i++) E.pos[i] += (double)dpos[i];
+        for (int i = 0; i < 3; i++) E.pos[i] = W.parked[i] + (double)dpos[i];
     }
     if (ghost) return;
     env_load_rest(S, e, lane, E);
@@ -746,7 +757,7 @@ __global__ void __launch_bounds__(BLOCK, 3) aba_substep_kernel(const DevModel* g
     if (lane < 6 || lane >= ND) q_dof = 0.f;
     float v_dof = lane < ND ? ve[lane] : 0.f;
     float t = (lane >= 6 && lane < ND) ? tau[(size_t)e * NJ + lane - 6] : 0.f;
-    float acc = dynamics_warp(M, W, quat, q_dof, v_dof, t, lane, nullptr);
+    float acc = dynamics_warp<false>(M, W, quat, q_dof, v_dof, t, lane, nullptr);
     float vn = v_dof + M.dt * acc;
     vn = fminf(fmaxf(vn, -M.max_coord_vel), M.max_coord_vel);
     if (lane >= ND) vn = 0.f;
@@ -827,10 +838,27 @@ static void fill_model(DevModel& D, const ss_model& m, const ss_params& p) {
         D.damping[j] = (float)m.joint_damping[j]; D.pd_p[j] = (float)m.pd_p[j]; D.pd_d[j] = (float)m.pd_d[j];
         D.init_q[j] = (float)m.init_q[j];
     }
-    for (int c = 0; c < SS_NCOL; c++) {
-        for (int k = 0; k < 3; k++) { D.col_p0[c][k] = (float)m.col_p0[c][k]; D.col_p1[c][k] = (float)m.col_p1[c][k]; }
-        D.col_radius[c] = (float)m.col_radius[c]; D.col_body[c] = m.col_body[c]; D.col_foot[c] = m.col_foot[c];
+    D.n_geom = m.n_geom; D.n_pair = m.n_pair; D.collision_mode = p.collision_mode; D.self_cross_terms = p.self_cross_terms;
+    D.n_scand = 0;
+    for (int g = 0; g < m.n_geom; g++) {
+        double len2 = 0;
+        for (int k = 0; k < 3; k++) {
+            D.geom_p0[g][k] = (float)m.geom_p0[g][k]; D.geom_p1[g][k] = (float)m.geom_p1[g][k];
+            len2 += (m.geom_p1[g][k] - m.geom_p0[g][k]) * (m.geom_p1[g][k] - m.geom_p0[g][k]);
+        }
+        D.geom_radius[g] = (float)m.geom_radius[g]; D.geom_half[g] = (float)(0.5 * sqrt(len2) * 1.0001 + 1e-6);
+        D.geom_breaking[g] = (float)m.geom_breaking[g]; D.geom_body[g] = (unsigned char)m.geom_body[g];
     }
+    // stone candidate table, pass by pass: feet (always), then -- collision_mode >= 1 -- the other capsules and the spheres
+    for (int g = 0; g < m.n_geom; g++) {
+        if (!m.geom_stone[g] || (p.collision_mode == 0 && m.geom_foot[g] < 0)) continue;
+        for (int slot = 0; slot < 4; slot++)
+            for (int end = 0; end < (m.geom_sphere[g] ? 1 : 2); end++)
+                D.scand[D.n_scand++] = (unsigned short)(g | (slot << 5) | (end << 7));
+    }
+    for (int k = 0; k < m.n_pair; k++) { D.pair_a[k] = (unsigned char)m.pair_a[k]; D.pair_b[k] = (unsigned char)m.pair_b[k]; }
+    D.stone_breaking = (float)p.stone_breaking; D.self_friction = (float)p.self_friction; D.self_erp = (float)p.self_erp;
+    D.stone_radius = (float)(sqrt(p.stone_half[0] * p.stone_half[0] + p.stone_half[1] * p.stone_half[1] + p.stone_half[2] * p.stone_half[2]) * 1.0001);
     for (int f = 0; f < 2; f++) { D.foot_body[f] = m.foot_body[f]; for (int k = 0; k < 3; k++) D.foot_ref[f][k] = (float)m.foot_ref[f][k]; }
     D.contact_breaking = (float)m.contact_breaking; D.gravity = (float)p.gravity; D.dt = (float)p.dt; D.erp_limit = (float)p.erp_limit;
     double kd = p.dt * p.contact_stiffness + p.contact_damping;
@@ -856,7 +884,8 @@ static void fill_model(DevModel& D, const ss_model& m, const ss_params& p) {
 static int grid_for(int n) { return (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
 
 static int configure_kernels(size_t smem) {
-    CK(cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(temp_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -903,7 +932,11 @@ int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t
     CK(cudaMalloc(&E->cdf, (size_t)SS_GRID_CELLS * sizeof(double)));
     S.cdf = E->cdf;
     CK(cudaMemset(S.sv, 0, N * 64 * sizeof(float)));
-    CK(cudaMemset(S.warm, 0, N * SS_NWARM * sizeof(float)));
+    {
+        std::vector<float> w(N * SS_NWARM, 0.f);
+        for (size_t i = 0; i < N; i++) for (int k = 0; k < SS_MAX_CONTACTS; k++) w[i * SS_NWARM + k] = -1.f;
+        CK(cudaMemcpy(S.warm, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(S.terrain, 0, N * E->n_steps * 6 * sizeof(double)));
     CK(cudaMemset(S.plank, 0, N * E->rendered * 6 * sizeof(double)));
     CK(cudaMemset(S.scal, 0, N * SS_NSCAL * sizeof(double)));
@@ -960,8 +993,12 @@ int ss_reset_all(ss_env* E, float* obs_dev, void* stream) {
 static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el,
                        cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr) {
     if (e_end < 0) e_end = E->n;
-    env_step_kernel<<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
-                                                                       e_begin, e_end, packed);
+    if (E->S.dbg || E->S.trace_q)
+        env_step_kernel<true><<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
+                                                                                 e_begin, e_end, packed);
+    else
+        env_step_kernel<false><<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
+                                                                                  e_begin, e_end, packed);
     E->launches++;
     CK(cudaGetLastError());
     return SS_OK;

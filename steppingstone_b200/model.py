@@ -26,6 +26,7 @@ import xml.etree.ElementTree as ET
 import numpy as np
 
 NB, NJ, NDOF, NQ, NCOL, GRID = 22, 21, 27, 28, 4, 11
+NGEOM, MAX_PAIRS = 22, 160
 PARENT = [-1, 0, 1, 2, 3, 4, 5, 6, 7, 3, 9, 10, 11, 12, 0, 14, 15, 16, 0, 18, 19, 20]
 JOINT_NAMES = [
     "abdomen_z", "abdomen_y", "abdomen_x",
@@ -59,6 +60,12 @@ class SSModel(ctypes.Structure):
         ("contact_breaking", ctypes.c_double),
         ("init_q", ctypes.c_double * NJ), ("init_pos", ctypes.c_double * 3),
         ("total_mass", ctypes.c_double),
+        ("n_geom", ctypes.c_int32), ("n_pair", ctypes.c_int32),
+        ("geom_body", ctypes.c_int32 * NGEOM), ("geom_foot", ctypes.c_int32 * NGEOM),
+        ("geom_stone", ctypes.c_int32 * NGEOM), ("geom_sphere", ctypes.c_int32 * NGEOM),
+        ("geom_radius", ctypes.c_double * NGEOM), ("geom_p0", ctypes.c_double * 3 * NGEOM),
+        ("geom_p1", ctypes.c_double * 3 * NGEOM), ("geom_breaking", ctypes.c_double * NGEOM),
+        ("pair_a", ctypes.c_int32 * MAX_PAIRS), ("pair_b", ctypes.c_int32 * MAX_PAIRS),
     ]
 
 
@@ -78,7 +85,7 @@ class SSParams(ctypes.Structure):
         ("n_steps", ctypes.c_int32), ("rendered", ctypes.c_int32),
         ("stop_frames", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32),
         ("n_phantoms", ctypes.c_int32), ("use_sampler", ctypes.c_int32),
-        ("actuator_mode", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("actuator_mode", ctypes.c_int32), ("collision_mode", ctypes.c_int32),
         ("done_height", ctypes.c_double), ("electricity_cost", ctypes.c_double),
         ("stall_torque_cost", ctypes.c_double), ("joints_at_limit_cost", ctypes.c_double),
         ("step_radius", ctypes.c_double), ("r_max", ctypes.c_double),
@@ -87,6 +94,8 @@ class SSParams(ctypes.Structure):
         ("yaw_samples", ctypes.c_double * GRID), ("pitch_samples", ctypes.c_double * GRID),
         ("r_samples", ctypes.c_double * GRID), ("xtilt_samples", ctypes.c_double * GRID),
         ("ytilt_samples", ctypes.c_double * GRID),
+        ("self_friction", ctypes.c_double), ("self_erp", ctypes.c_double), ("stone_breaking", ctypes.c_double),
+        ("self_cross_terms", ctypes.c_int32), ("reserved1", ctypes.c_int32),
     ]
 
 
@@ -127,8 +136,9 @@ def _shortest_arc_z_to(d):
 
 
 class _Geom:
-    def __init__(self, kind, radius, p0, p1, name):
+    def __init__(self, kind, radius, p0, p1, name, contype=3, conaffinity=3):
         self.kind, self.radius, self.p0, self.p1, self.name = kind, radius, p0, p1, name
+        self.contype, self.conaffinity = contype, conaffinity
 
     def volume(self):
         r = self.radius
@@ -162,7 +172,7 @@ class _Link:
         self.joints, self.geoms, self.children = [], [], []
 
 
-def _parse_body(el):
+def _parse_body(el, gdef=(3, 3)):
     pos = _vec(el.get("pos", "0 0 0"), 3)
     rot = _quat_wxyz_to_mat(_vec(el.get("quat"), 4)) if el.get("quat") else np.eye(3)
     link = _Link(el.get("name"), pos, rot)
@@ -175,16 +185,17 @@ def _parse_body(el):
                                     pos=_vec(ch.get("pos", "0 0 0"), 3), lo=rng[0], hi=rng[1]))
         elif ch.tag == "geom":
             size = _vec(ch.get("size"))
+            ct, ca = int(ch.get("contype", gdef[0])), int(ch.get("conaffinity", gdef[1]))
             if ch.get("type") == "sphere":
                 p = _vec(ch.get("pos", "0 0 0"), 3)
-                link.geoms.append(_Geom("sphere", size[0], p, p.copy(), ch.get("name")))
+                link.geoms.append(_Geom("sphere", size[0], p, p.copy(), ch.get("name"), ct, ca))
             elif ch.get("type") == "capsule":
                 ft = _vec(ch.get("fromto"), 6)
-                link.geoms.append(_Geom("capsule", size[0], ft[:3], ft[3:], ch.get("name")))
+                link.geoms.append(_Geom("capsule", size[0], ft[:3], ft[3:], ch.get("name"), ct, ca))
             else:
                 raise ValueError("unsupported geom type %r" % ch.get("type"))
         elif ch.tag == "body":
-            link.children.append(_parse_body(ch))
+            link.children.append(_parse_body(ch, gdef))
     return link
 
 
@@ -227,8 +238,10 @@ def compile_mjcf(xml_path, robot_kind):
     assert root.find("compiler").get("angle") == "degree"
     jdef = root.find("default").find("joint")
     damping = float(jdef.get("damping"))
+    gdef_el = root.find("default").find("geom")
+    gdef = (int(gdef_el.get("contype", 1)), int(gdef_el.get("conaffinity", 1)))
     base_el = root.find("worldbody").find("body")
-    base = _parse_body(base_el)
+    base = _parse_body(base_el, gdef)
 
     T = dict(
         parent=np.array(PARENT, dtype=np.int32), depth=np.zeros(NB, np.int32),
@@ -240,10 +253,30 @@ def compile_mjcf(xml_path, robot_kind):
     I3 = [np.zeros((3, 3)) for _ in range(NB)]
     names = []
     geoms_of_body = {}
+    # every collision geom: (MJCF body name, our body index, p0, p1 in OUR body frame, geom); and the MJCF body tree
+    all_geoms = []
+    mj_parent = {}
+    link_disc = {}
+
+    def note_link(link, body_idx, offset, rot, parent_name):
+        mj_parent[link.name] = parent_name
+        for g in link.geoms:
+            all_geoms.append(dict(link=link.name, body=body_idx, p0=offset + rot @ g.p0, p1=offset + rot @ g.p1,
+                                  radius=g.radius, kind=g.kind, name=g.name))
+        if link.geoms:
+            # btCollisionShape::getAngularMotionDisc of the link's compound shape (about its inertial frame)
+            _, shift, _ = _link_inertial(link)
+            lo = np.full(3, np.inf); hi = np.full(3, -np.inf)
+            for g in link.geoms:
+                a, b = g.aabb(shift)
+                lo, hi = np.minimum(lo, a), np.maximum(hi, b)
+            link_disc[link.name] = 0.5 * np.linalg.norm(hi - lo) + np.linalg.norm(0.5 * (hi + lo))
+            link_filter[link.name] = (link.geoms[-1].contype, link.geoms[-1].conaffinity)   # the last geom wins
+    link_filter = {}
     foot_ref = {}
     mass_override = {"waist": 8.0} if robot_kind == 1 else {}     # robots.py:786-791
 
-    def add_fixed(body_idx, link, offset, rot):
+    def add_fixed(body_idx, link, offset, rot, parent_name):
         """Merge a jointless child (head, torso, hand) into body ``body_idx``; offset/rot place the child's
         frame in that body's frame."""
         m, c, I = _link_inertial(link, mass_override=mass_override.get(link.name))
@@ -251,11 +284,12 @@ def compile_mjcf(xml_path, robot_kind):
         I_b = rot @ I @ rot.T
         T["mass"][body_idx], T["com"][body_idx], I3[body_idx] = _merge(
             T["mass"][body_idx], T["com"][body_idx], I3[body_idx], m, c_b, I_b)
+        note_link(link, body_idx, offset, rot, parent_name)
         for ch in link.children:
             assert not ch.joints
-            add_fixed(body_idx, ch, offset + rot @ ch.pos, rot @ ch.rot)
+            add_fixed(body_idx, ch, offset + rot @ ch.pos, rot @ ch.rot, link.name)
 
-    def walk(link, parent_idx, parent_frame_origin_in_parent_mjcf):
+    def walk(link, parent_idx, parent_frame_origin_in_parent_mjcf, parent_name=None):
         """``parent_frame_origin_in_parent_mjcf``: where OUR frame of the parent body sits inside the
         parent's MJCF body frame (its last hinge anchor; zero for the base)."""
         if not link.joints:               # base
@@ -291,11 +325,12 @@ def compile_mjcf(xml_path, robot_kind):
             geoms_of_body[idx] = (link, my_origin)
             if link.name in ("right_foot", "left_foot"):
                 foot_ref[link.name] = (idx, c - my_origin)
+        note_link(link, idx, -my_origin, np.eye(3), parent_name)
         for ch in link.children:
             if ch.joints:
-                walk(ch, idx, my_origin)
+                walk(ch, idx, my_origin, link.name)
             else:
-                add_fixed(idx, ch, ch.pos - my_origin, ch.rot)
+                add_fixed(idx, ch, ch.pos - my_origin, ch.rot, link.name)
         return idx
 
     walk(base, -1, np.zeros(3))
@@ -329,6 +364,7 @@ def compile_mjcf(xml_path, robot_kind):
     disc = 0.5 * np.linalg.norm(hi - lo) + np.linalg.norm(0.5 * (hi + lo))
     T["contact_breaking"] = 0.02 * disc
 
+
     T["tau_max"] = np.array(TAU_W3D if robot_kind == 0 else TAU_MIKE, dtype=np.float64)
     T["pd_p"] = np.array(PD_P, dtype=np.float64)
     T["pd_d"] = T["pd_p"] / 10.0
@@ -343,6 +379,79 @@ def compile_mjcf(xml_path, robot_kind):
     T["init_pos"] = np.array([0.3, 0.0, 1.25 if robot_kind == 0 else 1.0])
     T["total_mass"] = float(T["mass"].sum())
     T["body_names"] = names
+
+    # ---- collision geoms of every link (URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS, robots.py:496-500) ----
+    # order: the four foot capsules first (same numbering as col_*), then the other capsules, then the spheres
+    def order_key(g):
+        foot = g["link"] in ("right_foot", "left_foot")
+        return (0 if foot else (1 if g["kind"] == "capsule" else 2))
+    geoms = sorted(all_geoms, key=order_key)          # stable: XML order inside each class
+    feet = [g for g in geoms if g["link"] in ("right_foot", "left_foot")]
+    assert [g["body"] for g in feet] == list(col_body)
+    assert len(geoms) <= NGEOM
+    STATIC_GROUP, STATIC_MASK = 2, -1 ^ 2             # btBroadphaseProxy::StaticFilter, AllFilter ^ StaticFilter
+
+    def ancestors(name):
+        out = []
+        while mj_parent.get(name) is not None:
+            name = mj_parent[name]; out.append(name)
+        return out
+    G = dict(geom_body=np.zeros(NGEOM, np.int32), geom_foot=np.full(NGEOM, -1, np.int32), geom_stone=np.zeros(NGEOM, np.int32),
+             geom_sphere=np.zeros(NGEOM, np.int32), geom_radius=np.zeros(NGEOM), geom_p0=np.zeros((NGEOM, 3)),
+             geom_p1=np.zeros((NGEOM, 3)), geom_breaking=np.zeros(NGEOM))
+    for k, g in enumerate(geoms):
+        grp, msk = link_filter[g["link"]]
+        G["geom_body"][k] = g["body"]
+        G["geom_foot"][k] = {"right_foot": 0, "left_foot": 1}.get(g["link"], -1)
+        G["geom_stone"][k] = int(bool(grp & STATIC_MASK) and bool(STATIC_GROUP & msk))
+        G["geom_sphere"][k] = int(g["kind"] == "sphere")
+        G["geom_radius"][k] = g["radius"]; G["geom_p0"][k] = g["p0"]; G["geom_p1"][k] = g["p1"]
+        G["geom_breaking"][k] = 0.02 * link_disc[g["link"]]
+    pa, pb = [], []
+    for i in range(len(geoms)):
+        for j in range(i + 1, len(geoms)):
+            a, b = geoms[i], geoms[j]
+            if a["link"] == b["link"] or a["body"] == b["body"]:
+                continue                               # same link, or rigidly attached to the same body (constant distance)
+            if a["link"] in ancestors(b["link"]) or b["link"] in ancestors(a["link"]):
+                continue                               # btMultiBodyLinkCollider: BT_MULTIBODYLINKFLAGS_DISABLE_ALL_PARENT_COLLISION
+            (ga, ma), (gb, mb) = link_filter[a["link"]], link_filter[b["link"]]
+            if not ((ga & mb) and (gb & ma)):
+                continue                               # contype / conaffinity (walker3d.xml:5,21,28,31)
+            pa.append(i); pb.append(j)
+    assert len(pa) <= MAX_PAIRS, len(pa)
+    # order the pairs by how close they can get (smallest gap over random poses first): the GPU evaluates them 32 at a
+    # time and skips a whole batch when none of its pairs is within reach, so likely pairs go first
+    def fk_points(qj):
+        Rw = [np.eye(3)] * NB; ow = [np.zeros(3)] * NB
+        for b in range(1, NB):
+            pr = PARENT[b]; ax = T["axis"][b]; th = qj[b - 1]
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            Rj = np.eye(3) + math.sin(th) * K + (1 - math.cos(th)) * (K @ K)
+            Rw[b] = Rw[pr] @ T["R0"][b].reshape(3, 3) @ Rj
+            ow[b] = ow[pr] + Rw[pr] @ T["anchor"][b]
+        return [(ow[g["body"]] + Rw[g["body"]] @ g["p0"], ow[g["body"]] + Rw[g["body"]] @ g["p1"]) for g in geoms]
+
+    def seg_dist(p1, q1, p2, q2):
+        best = np.inf
+        for s in np.linspace(0, 1, 5):
+            for t in np.linspace(0, 1, 5):
+                best = min(best, np.linalg.norm(p1 + s * (q1 - p1) - p2 - t * (q2 - p2)))
+        return best
+    rng = np.random.RandomState(0)
+    gap = np.full(len(pa), np.inf)
+    for k in range(60):
+        qj = T["init_q"] if k == 0 else rng.uniform(T["q_lo"], T["q_hi"])
+        pts = fk_points(qj)
+        for n, (i, j) in enumerate(zip(pa, pb)):
+            gap[n] = min(gap[n], seg_dist(*pts[i], *pts[j]) - geoms[i]["radius"] - geoms[j]["radius"])
+    order = np.argsort(gap, kind="stable")
+    pa = [pa[k] for k in order]; pb = [pb[k] for k in order]
+    G["pair_a"] = np.zeros(MAX_PAIRS, np.int32); G["pair_b"] = np.zeros(MAX_PAIRS, np.int32)
+    G["pair_a"][:len(pa)] = pa; G["pair_b"][:len(pb)] = pb
+    G["n_geom"] = len(geoms); G["n_pair"] = len(pa)
+    G["geom_names"] = [g["name"] for g in geoms]
+    T.update(G)
     return T
 
 
@@ -366,7 +475,10 @@ def default_params(robot_kind, terrain_mode=None):
         stop_frames=30, max_episode_steps=1000,
         n_phantoms=20 if robot_kind == 0 else 0,                     # walker3d_envs.py:489,566 / mike.py:32
         use_sampler=0 if robot_kind == 0 else 1,                     # walker3d_envs.py:1083 / mike.py:593
-        actuator_mode=0, reserved0=0,
+        actuator_mode=0, collision_mode=2,                           # robots.py:496-500: self-collision on
+        self_friction=1.2 * 1.2, self_erp=0.9,                       # walker3d.xml:5; bullet_utils.py:324
+        stone_breaking=0.02 * (0.0125 + math.sqrt(0.25 ** 2 + 0.375 ** 2 + 0.125 ** 2)),
+        self_cross_terms=0, reserved1=0,
         done_height=0.7, electricity_cost=4.5, stall_torque_cost=0.225, joints_at_limit_cost=0.1,
         step_radius=0.25, r_max=1.5, tilt_limit_deg=0.0,
         mirror_prob=0.0 if robot_kind == 0 else 0.5,                 # robots.py:583 / :846
@@ -405,9 +517,12 @@ def load_tables(robot_kind):
         raw = json.load(f)
     T = {}
     for k, v in raw.items():
-        if k == "body_names":
+        if k in ("body_names", "geom_names"):
             T[k] = v
-        elif k in ("parent", "depth", "col_body", "col_foot", "foot_body"):
+        elif k in ("n_geom", "n_pair"):
+            T[k] = int(v)
+        elif k in ("parent", "depth", "col_body", "col_foot", "foot_body", "geom_body", "geom_foot", "geom_stone",
+                   "geom_sphere", "pair_a", "pair_b"):
             T[k] = np.array(v, dtype=np.int32)
         elif isinstance(v, list):
             T[k] = np.array(v, dtype=np.float64)

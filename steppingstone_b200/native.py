@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libss_b200.so")
 INCLUDE = os.path.join(REPO_DIR, "include")
 
-NQ, ND, NJ, OBS, NWARM, NSCAL, NINT, MTW, GRID_CELLS = 28, 27, 21, 60, 32, 16, 8, 625, 11 ** 5
+NQ, ND, NJ, OBS, NWARM, NSCAL, NINT, MTW, GRID_CELLS = 28, 27, 21, 60, 16, 16, 8, 625, 11 ** 5
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -247,6 +247,39 @@ def run_b200(args, wl):
         abaL_ms.append(a.elapsed_time(b))
     abaL_s = float(np.mean(abaL_ms)) * 1e-3
 
+    # ---- create_temp_states fill kernel (value-guided sampling probes): the one HBM-bound kernel of the path,
+    #      240 B written per (env, grid cell); 48 envs x 161051 cells = 1.86 GB per launch (> L2, no flush needed) ----
+    tsf = None
+    try:
+        env_t = BatchedStepperEnv(WORKLOADS["mike"]["env_id"], 8, 48, device=local, output="torch")
+        env_t.update_curriculum(5)
+        env_t.reset()
+        st = env_t.get_state()
+        st["ints"][:, 5] = 1                                   # update_terrain flag: every env produces its grid
+        env_t.set_state(st)
+        import ctypes as _ct
+        from steppingstone_b200 import native as _nat, seeding as _seed
+        cells = 11 ** 5
+        out_t = torch.empty((48, cells, 60), dtype=torch.float32, device=dev)
+        grid_t = _seed.fake_sample_grid()
+        def _fill():
+            _nat.check(env_t._lib.ss_create_temp_states(env_t._h, 5, grid_t.ctypes.data, None, out_t.data_ptr(), env_t._stream()), "ss_create_temp_states")
+        for _ in range(3):
+            _fill()
+        torch.cuda.synchronize(dev)
+        ts_ms = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); _fill(); b.record(); torch.cuda.synchronize(dev)
+            ts_ms.append(a.elapsed_time(b))
+        ts_s = float(np.mean(ts_ms)) * 1e-3
+        tsf = {"envs": 48, "cells": cells, "bytes": 48 * cells * 240, "avg_launch_ms": ts_s * 1e3,
+               "achieved": 48 * cells * 240 / ts_s / 1e9}
+        del out_t
+        env_t.close()
+    except Exception as exc:                                  # never let the side measurement break the bench line
+        tsf = {"error": repr(exc)[:200]}
+
     peak, peak_src = measured_peaks()
     kern_s = t_dev / K
     achieved = ALG_BYTES_PER_ENV_STEP * N / kern_s / 1e9
@@ -289,6 +322,11 @@ def run_b200(args, wl):
                                              "achieved": ALG_BYTES_PER_ENV_SUBSTEP * NL / abaL_s / 1e9,
                                              "frac": ALG_BYTES_PER_ENV_SUBSTEP * NL / abaL_s / 1e9 / peak}},
         }
+        if tsf is not None:
+            if "achieved" in tsf:
+                tsf.update(kernel="temp_prep_kernel + temp_fill_kernel", bound="hbm", peak=peak, unit="GB/s", frac=tsf["achieved"] / peak,
+                           algorithmic_bytes_per_env_cell=240)
+            line["roofline_temp_states"] = tsf
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

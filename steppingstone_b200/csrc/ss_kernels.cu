@@ -109,6 +109,7 @@ __device__ __forceinline__ void env_load_rest(const DevState& S, int e, int lane
     E.ep_ret = sc[SS_S_EP_RET];
     E.cache_contact[0] = (float)sc[SS_S_CACHE_CONTACT0]; E.cache_contact[1] = (float)sc[SS_S_CACHE_CONTACT1];
     const int* it = S.ints + (size_t)e * SS_NINT;
+    E.next_step = it[SS_I_NEXT_STEP];      // again: not carried in a register through the physics
     E.reached = it[SS_I_REACHED_COUNT]; E.mirrored = it[SS_I_MIRRORED];
     E.elapsed = it[SS_I_ELAPSED]; E.ep_len = it[SS_I_EP_LEN]; E.update_terrain = it[SS_I_UPDATE_TERRAIN];
     E.phantom_idx = it[SS_I_PHANTOM_IDX]; E.started = it[SS_I_STARTED];
@@ -506,11 +507,10 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     Env E; env_load_phys(S, e, lane, E);
 
     // robots.py:289-293 apply_action (torque held over the control step) + MJCF joint damping torque
-    float a_raw = 0.f, tau = 0.f;
+    float tau = 0.f;
     if (lane >= 6 && lane < ND) {
         int j = lane - 6;
-        a_raw = act[(size_t)e * NJ + j];
-        float x = fminf(fmaxf(a_raw, -1.f), 1.f);
+        float x = fminf(fmaxf(act[(size_t)e * NJ + j], -1.f), 1.f);
         if (M.actuator_mode == 0) tau = M.tau_max[j] * x;
         else {                                                                     // robots.py:486-493 (opt-in PD)
             float lo = M.q_lo[j], hi = M.q_hi[j];
@@ -564,7 +564,10 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     if (!(-0.2f < rpy[1] && rpy[1] < 0.4f)) posture = fabsf(rpy[1]);
     if (!(-0.4f < rpy[0] && rpy[0] < 0.4f)) posture += fabsf(rpy[0]);
     float m1 = 0.f, m2 = 0.f;
-    if (lane >= 6 && lane < ND) { m1 = fabsf(a_raw * 0.1f * E.v_dof); m2 = a_raw * a_raw; }      // unclipped action (q5)
+    if (lane >= 6 && lane < ND) {                                                               // unclipped action (q5)
+        const float a_again = act[(size_t)e * NJ + lane - 6];      // re-read (L1/L2 hit): keeps a register free through the physics
+        m1 = fabsf(a_again * 0.1f * E.v_dof); m2 = a_again * a_again;
+    }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) { m1 += __shfl_xor_sync(FULL, m1, off); m2 += __shfl_xor_sync(FULL, m2, off); }
     float energy = M.electricity_cost * (m1 / NJ) + M.stall_torque_cost * (m2 / NJ);

@@ -15,17 +15,19 @@
 
 namespace ssb {
 
-// CTA shape of the env kernels.  The substep loop is ~8k straight-line instructions (128 KB): warps that drift apart
-// thrash the instruction caches (ncu: stall_no_instruction was the top stall).  8 warps per CTA re-aligned by one
-// __syncthreads() per substep share their instruction fetches: 7.2M -> 10.2M env-steps/s at N=8192 (profiles/).
+// CTA shape of the env kernels.  The substep loop is ~9k straight-line instructions (144 KB): warps that drift apart
+// thrash the instruction caches (ncu: stall_no_instruction was the top stall).  The warps of a CTA are re-aligned by one
+// __syncthreads() per substep so that they share their instruction fetches (without it the kernel is 1.6x slower).
+// ONE CTA of 20 warps per SM (96 registers, 210 KB shared memory): all resident warps of an SM move in step
+// (2 CTAs of 10 warps: 0.826 ms; 1 CTA of 20: 0.802 ms at N=8192; profiles/README.md).
 #ifndef SS_WPB
-#define SS_WPB 10
+#define SS_WPB 20
 #endif
 #ifndef SS_SYNC
 #define SS_SYNC 1
 #endif
 #ifndef SS_MINB
-#define SS_MINB 2
+#define SS_MINB 1
 #endif
 constexpr int WARPS_PER_BLOCK = SS_WPB;
 constexpr int SS_REC = 64;       // floats per env in the packed result record of the host-buffer path
@@ -38,11 +40,13 @@ struct alignas(16) BlockSmem {
     WarpSmem W[WARPS_PER_BLOCK];
 };
 
+constexpr int ABA_WPB = 8;        // the stand-alone forward-dynamics kernel: 8-warp CTAs, 3 per SM (80 registers)
+constexpr int ABA_BLOCK = 32 * ABA_WPB;
 struct alignas(16) BlockSmemDyn {
     DevModel M;
     unsigned long long bar;
     unsigned long long pad;
-    WarpSmemDyn W[WARPS_PER_BLOCK];
+    WarpSmemDyn W[ABA_WPB];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -740,13 +744,13 @@ __global__ void __launch_bounds__(TS_CELLS) temp_fill_kernel(const DevModel* gm,
 }
 
 // stand-alone forward-dynamics substep: q [N,28], qd [N,27], tau [N,21] f32 -> q, qd in place (524 B / env-substep)
-__global__ void __launch_bounds__(BLOCK, 3) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
+__global__ void __launch_bounds__(ABA_BLOCK, 3) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
                                                                const float* __restrict__ tau, int n) {
     BlockSmemDyn& B = *reinterpret_cast<BlockSmemDyn*>(smem_raw);
     stage_model(B, gm);
     const DevModel& M = B.M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int e = blockIdx.x * ABA_WPB + warp;
     if (e >= n) return;
     WarpSmemDyn& W = B.W[warp];
     float* qe = q + (size_t)e * SS_NQ; float* ve = qd + (size_t)e * ND;
@@ -1257,7 +1261,7 @@ int ss_debug_read(ss_env* E, float* out_host) {
 int ss_aba_substep(ss_env* E, float* q_dev, float* qd_dev, const float* tau_dev, int32_t n, void* stream) {
     if (!E || !q_dev || !qd_dev || !tau_dev || n <= 0) return fail(SS_ERR_ARG, "ss_aba_substep: bad argument");
     CK(cudaSetDevice(E->device));
-    aba_substep_kernel<<<grid_for(n), BLOCK, sizeof(BlockSmemDyn), (cudaStream_t)stream>>>(E->dm, q_dev, qd_dev, tau_dev, n);
+    aba_substep_kernel<<<(n + ABA_WPB - 1) / ABA_WPB, ABA_BLOCK, sizeof(BlockSmemDyn), (cudaStream_t)stream>>>(E->dm, q_dev, qd_dev, tau_dev, n);
     E->launches++;
     CK(cudaGetLastError());
     return SS_OK;

@@ -91,6 +91,9 @@ def main():
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--seed", type=int, default=8)
     ap.add_argument("--curriculum", type=int, default=0)
+    ap.add_argument("--use-curriculum", action="store_true",
+                    help="train.py:503-506: raise the terrain curriculum when the mean episode return passes 1000")
+    ap.add_argument("--lr-decay", type=float, default=0.99, help="per 40000 frames, floor 3e-5 (train.py:215-216)")
     ap.add_argument("--terrain-mode", type=int, default=None)
     ap.add_argument("--minutes", type=float, default=0.0, help="stop after this many minutes (0 = run all iterations)")
     args = ap.parse_args()
@@ -105,7 +108,11 @@ def main():
     rollouts.observations[0].copy_(envs.reset())
     num_mini_batch = max(1, args.envs * args.steps // args.mini_batch)
     t_start = time.time(); frames = 0
+    curriculum = args.curriculum
     for it in range(args.iters):
+        lr = max(args.lr * args.lr_decay ** (frames / 40000.0), 3e-5)
+        for g in opt.param_groups:
+            g["lr"] = lr
         stats = EpisodeStats(dev)
         t0 = time.time()
         collect_rollout(envs, ac, rollouts, args.steps, stats)
@@ -120,9 +127,12 @@ def main():
         mean_r, n_ep = stats.mean()
         mean_l = float(stats.len_sum.item()) / max(n_ep, 1)
         print("iter %4d frames %9d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  value_loss %8.3f  "
-              "collect %.0f env-steps/s (incl. policy)  update %.2fs" % (
-                  it, frames, n_ep, mean_r, mean_l, float(rollouts.rewards.mean()), vl,
+              "curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy)  update %.2fs" % (
+                  it, frames, n_ep, mean_r, mean_l, float(rollouts.rewards.mean()), vl, curriculum, lr,
                   args.envs * args.steps / (t1 - t0), t2 - t1), flush=True)
+        if args.use_curriculum and n_ep > 0 and mean_r > 1000 and curriculum <= 4:      # train.py:503-506
+            curriculum += 1
+            envs.update_curriculum(curriculum)
         if args.minutes and time.time() - t_start > args.minutes * 60:
             break
     envs.close()

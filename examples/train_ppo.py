@@ -126,9 +126,11 @@ def main():
         frames += args.envs * args.steps
         mean_r, n_ep = stats.mean()
         mean_l = float(stats.len_sum.item()) / max(n_ep, 1)
-        print("iter %4d frames %9d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  value_loss %8.3f  "
+        # stones reached per 1000 env-steps: a step carrying the step bonus (50 exp(-d/0.25), walker3d_envs.py:1001-1006)
+        stones = float((rollouts.rewards > 10.0).sum().item()) / (args.envs * args.steps) * 1000.0
+        print("iter %4d frames %9d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  stones/1000steps %5.2f  value_loss %8.3f  "
               "curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy)  update %.2fs" % (
-                  it, frames, n_ep, mean_r, mean_l, float(rollouts.rewards.mean()), vl, curriculum, lr,
+                  it, frames, n_ep, mean_r, mean_l, float(rollouts.rewards.mean()), stones, vl, curriculum, lr,
                   args.envs * args.steps / (t1 - t0), t2 - t1), flush=True)
         if args.use_curriculum and n_ep > 0 and mean_r > 1000 and curriculum <= 4:      # train.py:503-506
             curriculum += 1

@@ -40,7 +40,13 @@ struct alignas(16) BlockSmem {
     WarpSmem W[WARPS_PER_BLOCK];
 };
 
-constexpr int ABA_WPB = 8;        // the stand-alone forward-dynamics kernel: 8-warp CTAs, 3 per SM (80 registers)
+#ifndef SS_ABA_WPB
+#define SS_ABA_WPB 8
+#endif
+#ifndef SS_ABA_MINB
+#define SS_ABA_MINB 4
+#endif
+constexpr int ABA_WPB = SS_ABA_WPB;   // the stand-alone forward-dynamics kernel: 8-warp CTAs, 4 per SM (64 registers; 3 per SM / 80 registers is 7 % slower)
 constexpr int ABA_BLOCK = 32 * ABA_WPB;
 struct alignas(16) BlockSmemDyn {
     DevModel M;
@@ -744,7 +750,7 @@ __global__ void __launch_bounds__(TS_CELLS) temp_fill_kernel(const DevModel* gm,
 }
 
 // stand-alone forward-dynamics substep: q [N,28], qd [N,27], tau [N,21] f32 -> q, qd in place (524 B / env-substep)
-__global__ void __launch_bounds__(ABA_BLOCK, 3) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
+__global__ void __launch_bounds__(ABA_BLOCK, SS_ABA_MINB) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
                                                                const float* __restrict__ tau, int n) {
     BlockSmemDyn& B = *reinterpret_cast<BlockSmemDyn*>(smem_raw);
     stage_model(B, gm);

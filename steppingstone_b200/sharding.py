@@ -32,14 +32,19 @@ ROLLOUT_FIELDS = ("observations", "states", "rewards", "value_preds", "returns",
 
 def gather_rollout(rollouts, group=None, fields=ROLLOUT_FIELDS):
     """All-gather the [T(+1), N_local, ...] rollout tensors along the env axis -> dict of [T(+1), N_total, ...].
-    Shards must be equal-sized (N_total divisible by the world size), as in BASELINE config 4 (8 x 8192)."""
+    Shards must be equal-sized (N_total divisible by the world size), as in BASELINE config 4 (8 x 8192).
+    One ``all_gather_into_tensor`` per field into a [world, T, N_local, ...] buffer (NCCL writes every peer's shard
+    straight into place), then one strided copy to put the env axis second."""
     world = dist.get_world_size(group)
     out = {}
     for name in fields:
         t = getattr(rollouts, name).contiguous()
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t, group=group)
-        out[name] = torch.cat(parts, dim=1)
+        buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(buf, t, group=group)
+        else:                                         # gloo (CPU tests): list form
+            dist.all_gather(list(buf.unbind(0)), t, group=group)
+        out[name] = buf.transpose(0, 1).reshape(t.shape[0], world * t.shape[1], *t.shape[2:])
     return out
 
 

@@ -76,7 +76,7 @@ constexpr int DBG_H = 0, DBG_C = 729, DBG_CAND = 756, DBG_ROWS = 756 + 256, DBG_
 
 // per-warp scratch
 struct alignas(16) WarpSmem {
-    float S[NB][6];
+    float S[NB][8];           // hinge motion vectors (6) padded to 32 bytes: two LDS.128 per body
     float pose[NB][12];       // body poses of this substep: R (9, to world axes), origin rel. the base origin (3)
     float gw[SS_NGEOM][8];    // geom segments in the common frame: p0 (3), p1 (3), radius, pad
     float stone[4][16];       // per candidate slot: box centre rel. step-start base pos (3), R (9), valid, pad
@@ -95,7 +95,7 @@ static_assert(sizeof(((WarpSmem*)0)->u.d) >= 7 * SS_MAX_STONES * sizeof(double),
 
 // scratch of the dynamics-only kernel (aba_substep): same member names, no constraint-solver storage
 struct alignas(16) WarpSmemDyn {
-    float S[NB][6];
+    float S[NB][8];
     float pose[NB][12];
     float dinv[32];
     struct { struct { float H[HS * HS]; } s; } u;
@@ -257,8 +257,8 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
     float S[6] = { 0, 0, 0, 0, 0, 0 };
     if (isj) { matvec3(X.R, M.axis[lane], S); cross3(X.p, S, S + 3); }
     if (isb) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) W.S[lane][i] = S[i];
+        float4* Sp = reinterpret_cast<float4*>(W.S[lane]);
+        Sp[0] = make_float4(S[0], S[1], S[2], S[3]); Sp[1] = make_float4(S[4], S[5], 0.f, 0.f);
     }
     if (isb) {
 #pragma unroll
@@ -315,9 +315,9 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
         for (int it = 0; it < 8; it++) {
             j = (j == 9) ? 3 : ((j == 14 || j == 18 || j == 1) ? 0 : j - 1);
             if (j < 1) break;
-            float v = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) v += W.S[j][i] * F[i];
+            const float4* Sj = reinterpret_cast<const float4*>(W.S[j]);
+            const float4 s0 = Sj[0], s1 = Sj[1];
+            float v = s0.x * F[0] + s0.y * F[1] + s0.z * F[2] + s0.w * F[3] + s1.x * F[4] + s1.y * F[5];
             H[d * HS + 5 + j] = v; H[(5 + j) * HS + d] = v;
         }
 #pragma unroll
@@ -856,8 +856,9 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 z[0] = wr[0]; z[1] = wr[1]; z[2] = wr[2]; z[3] = dir[0]; z[4] = dir[1]; z[5] = dir[2];
 #pragma unroll
                 for (int i = 1; i < NB; i++) {
-                    const float* Si = W.S[i];
-                    float v = Si[0] * wr[0] + Si[1] * wr[1] + Si[2] * wr[2] + Si[3] * dir[0] + Si[4] * dir[1] + Si[5] * dir[2];
+                    const float4* Si = reinterpret_cast<const float4*>(W.S[i]);
+                    const float4 s0 = Si[0], s1 = Si[1];
+                    float v = s0.x * wr[0] + s0.y * wr[1] + s0.z * wr[2] + s0.w * dir[0] + s1.x * dir[1] + s1.y * dir[2];
                     z[5 + i] = ((mask >> i) & 1) ? v : 0.f;
                 }
             }

@@ -55,3 +55,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), "%s references the oracle" % f
+
+
+def _build_c_host(tmp):
+    import subprocess, sys
+    from steppingstone_b200 import native
+    native.build_native()
+    exe = os.path.join(tmp, "c_host")
+    libdir = os.path.join(ROOT, "steppingstone_b200")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "examples", "c_host.c"), "-L", libdir, "-lss_b200", "-Wl,-rpath," + libdir, "-lm"])
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "dump_tables.py"), os.path.join(tmp, "tables"), "walker3d", "64", "8"],
+                          stdout=subprocess.DEVNULL)
+    return exe, os.path.join(tmp, "tables")
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_c_host_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/ss_env.h is valid C, a plain-C host links against libss_b200.so, and without a GPU it gets an error code
+    and a message (no CPU fallback)."""
+    import subprocess
+    exe, tables = _build_c_host(str(tmp_path))
+    res = subprocess.run([exe, tables, "64", "4"], capture_output=True, text=True)
+    assert res.returncode == 1 and "no CUDA device" in res.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_runs_on_gpu(tmp_path):
+    import subprocess
+    exe, tables = _build_c_host(str(tmp_path))
+    res = subprocess.run([exe, tables, "64", "40"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "env-steps/s" in res.stdout and "episodes finished" in res.stdout

@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_PER_ENV_STEP = 884      # fused env-step boundary, fp32
 ALG_BYTES_PER_ENV_SUBSTEP = 524   # aba_substep kernel boundary, fp32
 H2D_PER_ENV = 21 * 4
-D2H_PER_ENV = 60 * 4 + 4 + 1 + 1 + 4 + 4
+D2H_PER_ENV = 64 * 4              # one packed result record per env: obs 60 f32, reward, episode return, length, done|timeout
 WORKLOADS = {
     "w3d-flat": dict(env_id="mocca_envs:Walker3DStepperEnv-v0", kind=0, terrain_mode=2, curriculum=None,
                      name="Walker3DStepperEnv-v0 flat-terrain stage, 240 Hz / 4 substeps, 20 PGS iters"),

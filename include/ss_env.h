@@ -83,7 +83,8 @@ int ss_step(ss_env* env, const float* act_dev, float* obs_dev, float* rew_dev, u
 
 /* Same call with HOST buffers (the reference's numpy-in / numpy-out contract, envs_utils.py:550-558, 608-620):
  * rew_host is float64 like the reference's stacked python floats, done_host / timeout_host are 0/1 bytes (numpy
- * bool storage).  Non-finite actions fail with SS_ERR_ARG before anything runs (robots.py:290).  Internally the batch
+ * bool storage).  A non-finite action fails with SS_ERR_ARG (robots.py:290: fatal in the reference too); slices of the
+ * batch in front of it have already stepped.  Internally the batch
  * is pipelined in slices (H2D -> kernel -> one packed D2H per slice, unpacked on the host while later slices run);
  * returns after everything has landed in the caller's arrays. */
 int ss_step_host(ss_env* env, const float* act_host, float* obs_host, double* rew_host,

@@ -1050,24 +1050,34 @@ int ss_step_host(ss_env* E, const float* act, float* obs, double* rew, uint8_t* 
     const int N = E->n;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now(), t_wait = 0, t_unpack = 0;
-    // robots.py:290 `assert np.isfinite(a).all()`: checked before anything is launched (read-only pass, then each slice
-    // is copied into the pinned buffer right before its H2D so that the GPU starts on slice 0 early)
-    {
-        const size_t cnt = (size_t)N * NJ;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(act);
-        uint32_t bad = 0;
-        for (size_t i = 0; i < cnt; i++) bad |= (uint32_t)((src[i] & 0x7f800000u) == 0x7f800000u);
-        if (bad) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
-    }
-    double t1 = now();
+    // Slices: equal shares except a short last one (its D2H + unpack is the only part not overlapped with GPU work).
     const int nslice = N >= 4096 ? SS_PIPE : (N >= 1024 ? 2 : 1);
     int b[SS_PIPE + 1];
-    for (int k = 0; k <= nslice; k++) b[k] = (int)((int64_t)N * k / nslice / WARPS_PER_BLOCK) * WARPS_PER_BLOCK;
-    b[nslice] = N;
+    {
+        static const int share[SS_PIPE + 1] = { 0, 28, 56, 84, 100 };      // cumulative percent, SS_PIPE == 4
+        for (int k = 0; k <= nslice; k++) {
+            int64_t cut = nslice == SS_PIPE ? (int64_t)N * share[k] / 100 : (int64_t)N * k / nslice;
+            b[k] = (int)(cut / WARPS_PER_BLOCK) * WARPS_PER_BLOCK;
+        }
+        b[nslice] = N;
+    }
+    double t1 = now();
+    // robots.py:290 `assert np.isfinite(a).all()` -- every worker of the reference asserts on ITS action inside step(), so a
+    // bad action is fatal there while other envs have already stepped.  Same here: each slice is checked on its way into
+    // the pinned buffer and launched at once (the GPU starts after the first slice, not after the whole batch); a
+    // non-finite action stops the call with SS_ERR_ARG, slices before it have stepped.
     for (int k = 0; k < nslice; k++) {
         cudaStream_t st = E->pipe[k];
-        const size_t n = (size_t)(b[k + 1] - b[k]);
-        memcpy(E->h_act + (size_t)b[k] * NJ, act + (size_t)b[k] * NJ, n * NJ * 4);
+        const size_t n = (size_t)(b[k + 1] - b[k]), cnt = n * NJ;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(act) + (size_t)b[k] * NJ;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(E->h_act) + (size_t)b[k] * NJ;
+        uint32_t bad = 0;
+        for (size_t i = 0; i < cnt; i++) { uint32_t u = src[i]; dst[i] = u; bad |= (uint32_t)((u & 0x7f800000u) == 0x7f800000u); }
+        if (bad) {
+            for (int j = 0; j < k; j++) cudaStreamSynchronize(E->pipe[j]);
+            E->launches -= k > 0 ? k - 1 : 0;
+            return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
+        }
         CK(cudaMemcpyAsync(E->d_act + (size_t)b[k] * NJ, E->h_act + (size_t)b[k] * NJ, n * NJ * 4, cudaMemcpyHostToDevice, st));
         rc = launch_step(E, E->d_act, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, 1, b[k], b[k + 1], E->d_rec); if (rc) return rc;
         CK(cudaMemcpyAsync(E->h_rec + (size_t)b[k] * SS_REC, E->d_rec + (size_t)b[k] * SS_REC, n * SS_REC * 4, cudaMemcpyDeviceToHost, st));

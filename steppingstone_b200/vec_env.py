@@ -86,6 +86,7 @@ class BatchedStepperEnv:
                                          ctypes.byref(self._h)), "ss_create")
         self._t0 = time.time()
         self._pending = None
+        self._no_infos = (_NO_INFO,) * self.num_envs
         self.curriculum = 0
         N = self.num_envs
         if output == "numpy":
@@ -135,8 +136,10 @@ class BatchedStepperEnv:
                 assert np.isfinite(a).all()                                     # robots.py:290
                 native.check(rc, "ss_step_host")
             # one shared empty dict for the envs that did not finish (train.py:446-454 only reads keys)
-            infos = [_NO_INFO] * N
             idx = np.flatnonzero(dones)
+            if idx.size == 0:
+                return obs, rew, dones, self._no_infos
+            infos = list(self._no_infos)
             if idx.size:                                                        # Monitor.update, envs_utils.py:136-151
                 t = round(time.time() - self._t0, 6)
                 rs = np.round(self._ep_ret[idx].astype(np.float64), 6).tolist()

@@ -496,6 +496,11 @@ def test_host_pipeline_matches_device_mode():
         gh.step(a)
     after = gh.get_state()
     assert np.array_equal(before["q"], after["q"]) and np.array_equal(before["ints"], after["ints"])
+    # a bad action in the LAST slice is refused too (the slices in front of it have stepped by then, as the workers of
+    # the reference would have: robots.py:290 asserts inside each worker's step)
+    a[5, 3] = 0.0; a[n - 1, 20] = np.inf
+    with pytest.raises(AssertionError):
+        gh.step(a)
 
 
 @pytest.mark.parametrize("kind", KINDS)

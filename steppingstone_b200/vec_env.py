@@ -181,16 +181,12 @@ class BatchedStepperEnv:
 
     def update_sample_prob(self, probs):
         """walker3d_envs.py:1317-1320 through envs_utils.py:568-571.  The reference sends one table per env;
-        train.py:269-271 broadcasts a single table, which is what the device keeps: ``probs`` may be one table
-        [11,11,11,11,11] or a stack [N,...] of identical tables."""
-        p = np.asarray(probs, dtype=np.float64)
-        if p.size == native.GRID_CELLS * self.num_envs:
-            p = p.reshape(self.num_envs, -1)
-            if not np.allclose(p, p[:1]):
-                raise NotImplementedError("per-env sampling tables are not supported: one table is shared by all envs")
-            p = p[0]
-        if p.size != native.GRID_CELLS:
-            raise ValueError("sample_prob must have 11^5 cells")
+        train.py:269-271 broadcasts a single table, which is what the device keeps: ``probs`` may be one table or a
+        stack [N, ...] of identical tables.  Accepted table shapes: the env's 5-D grid [11,11,11,11,11]
+        (yaw, pitch, r, x_tilt, y_tilt), and the 2-D [11,11] / 3-D [11,11,11] tables train.py:267-271, 311-315 build
+        (``update_sample_prob_1/_2``, walker3d_envs.py:1307-1315): those are embedded at index 0 of the missing axes --
+        every r / tilt sample of the stepper envs is the same value (mike.py:74-76), so this is the draw they mean."""
+        p = expand_sample_table(probs, self.num_envs)
         self._set_table(p, apply_now=True)
 
     def set_mirror(self, mirror):
@@ -344,6 +340,31 @@ class BatchedStepperEnv:
             self.close()
         except Exception:
             pass
+
+
+def expand_sample_table(probs, num_envs):
+    """One [11^5] sampling table from what callers pass to ``update_sample_prob`` (see there)."""
+    g = native.GRID_CELLS
+    p = np.asarray(probs, dtype=np.float64)
+    per_env = None
+    for cells in (11 ** 5, 11 ** 3, 11 ** 2):
+        if p.size == cells:
+            per_env = p.reshape(1, -1); break
+        if p.size == cells * num_envs and num_envs > 1:
+            per_env = p.reshape(num_envs, -1); break
+    if per_env is None:
+        raise ValueError("sample_prob must be a [11,11], [11,11,11] or [11,11,11,11,11] table (or one per env)")
+    if not np.allclose(per_env, per_env[:1]):
+        raise NotImplementedError("per-env sampling tables are not supported: one table is shared by all envs")
+    t = per_env[0]
+    if t.size == g:
+        return t
+    full = np.zeros((11,) * 5)
+    if t.size == 11 ** 2:
+        full[:, :, 0, 0, 0] = t.reshape(11, 11)
+    else:
+        full[:, :, :, 0, 0] = t.reshape(11, 11, 11)
+    return full.reshape(-1)
 
 
 def make_vec_envs(env_id, seed, num_processes, log_dir=None, **kwargs):

@@ -87,3 +87,21 @@ def test_c_host_runs_on_gpu(tmp_path):
     res = subprocess.run([exe, tables, "64", "40"], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     assert "env-steps/s" in res.stdout and "episodes finished" in res.stdout
+
+
+def test_sample_table_shapes():
+    """update_sample_prob accepts what train.py passes: [N,11,11] stacks (and 3-D / 5-D tables), one table shared."""
+    import numpy as np
+    from steppingstone_b200.vec_env import expand_sample_table
+    rng = np.random.RandomState(0)
+    t2 = rng.rand(11, 11); t2 /= t2.sum()
+    full = expand_sample_table(np.stack([t2] * 7), 7).reshape((11,) * 5)
+    assert np.array_equal(full[:, :, 0, 0, 0], t2) and full.sum() == pytest.approx(1.0) and np.count_nonzero(full) == 121
+    t3 = rng.rand(11, 11, 11)
+    assert np.array_equal(expand_sample_table(t3, 4).reshape((11,) * 5)[:, :, :, 0, 0], t3)
+    t5 = rng.rand(11 ** 5)
+    assert np.array_equal(expand_sample_table(t5, 3), t5)
+    with pytest.raises(NotImplementedError):
+        expand_sample_table(np.stack([t2, t2 * 2]), 2)
+    with pytest.raises(ValueError):
+        expand_sample_table(np.zeros(10), 2)

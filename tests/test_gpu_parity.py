@@ -564,3 +564,26 @@ def test_ragged_batch_sizes(n):
         assert ok.mean() >= 0.8 and np.array_equal(done_o.astype(bool)[ok], done_g[ok])
     sg = g.get_state()
     assert np.isfinite(sg["q"]).all() and np.isfinite(sg["qd"]).all()
+
+
+def test_checkpoint_resume_is_bit_exact(tmp_path):
+    """save_state / load_state: a restored env continues the rollout bit for bit (state, RNG streams, episode stats)."""
+    n = 96
+    a_env = make_gpu_env(1, n); a_env.update_curriculum(4)
+    a_env.reset()
+    rng = np.random.RandomState(2)
+    acts = [random_actions(rng, n, sd=0.5) for _ in range(40)]
+    for t in range(20):
+        a_env.step(acts[t])
+    path = str(tmp_path / "ckpt.npz")
+    a_env.save_state(path)
+    b_env = make_gpu_env(1, n); b_env.update_curriculum(4)
+    b_env.reset()
+    b_env.load_state(path)
+    for t in range(20, 40):
+        oa, ra, da, ia = a_env.step(acts[t]); ob, rb, db, ib = b_env.step(acts[t])
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db)
+        assert [i.get("episode", {}).get("l") for i in ia] == [i.get("episode", {}).get("l") for i in ib]
+    sa, sb = a_env.get_state(), b_env.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k

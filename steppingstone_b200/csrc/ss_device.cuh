@@ -1027,6 +1027,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
 #undef SS_ROW_STEP
         if (DIAG && dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
         // ---- velocity update: dv = L^-T sum_r w_r lam_r ----
+        __syncwarp();        // the w rows written above (lane = row) are read below with lane = dof
         float u = 0.f;
         auto gather = [&](int s0, int s1) {
             for (int s = s0; s < s1; s++) { float ls = shfl(lam, s); if (lane < ND) u = fmaf(Z[s * ZS + lane], ls, u); }

@@ -107,7 +107,8 @@ typedef struct ss_params {
     int32_t max_episode_steps; /* 1000 (__init__.py:126-136)                              */
     int32_t n_phantoms;        /* 20 / 0: RNG draws only (walker3d_envs.py:566-580)       */
     int32_t use_sampler;       /* Mike 1 (mike.py:593), W3D 0 (walker3d_envs.py:1083)     */
-    int32_t actuator_mode;     /* 0 torque held over the step (robots.py:289-293), 1 PD   */
+    int32_t actuator_mode;     /* 0 torque held over the step (robots.py:289-293), 1 the abandoned PD block of
+                                  robots.py:486-493 once per control step, 2 that PD law at every substep */
     int32_t collision_mode;    /* 0 feet vs stones only, 1 every link vs stones, 2 + self-collision (reference) */
     double done_height;        /* 0.7                                                     */
     double electricity_cost, stall_torque_cost, joints_at_limit_cost;

@@ -922,7 +922,11 @@ static void env_reset(const struct sso_env* S, env_t* e, float* obs) {
     e->elapsed = 0; e->ep_ret = 0; e->ep_len = 0; e->update_terrain = 0; e->started = 1;
 }
 
-static void apply_action(const ss_model* M, const ss_params* P, const env_t* e, const float* a, double* tau) {
+/* actuator_mode 0: the torque the env applies, tau_max * clip(a), held over the control step (robots.py:289-293);
+ * 1: the reference's abandoned PD block (robots.py:486-493), evaluated once per control step like it;
+ * 2: the same PD law re-evaluated at every physics substep ("per-substep PD joint torques", BASELINE north star).
+ * The MJCF joint damping torque is computed once per control step in every mode (PyBullet applies it per stepSimulation). */
+static void apply_action(const ss_model* M, const ss_params* P, const env_t* e, const float* a, double* tau, const double* damp_qd) {
     for (int j = 0; j < NJ; j++) {
         double x = a[j] < -1 ? -1 : (a[j] > 1 ? 1 : (double)a[j]);
         if (P->actuator_mode == 0) tau[j] = M->tau_max[j] * x;            /* robots.py:289-293 */
@@ -930,7 +934,7 @@ static void apply_action(const ss_model* M, const ss_params* P, const env_t* e, 
             double mid = 0.5 * (M->q_lo[j] + M->q_hi[j]), rel = 2 * (e->qj[j] - mid) / (M->q_hi[j] - M->q_lo[j]);
             tau[j] = M->pd_p[j] * (x - rel) - M->pd_d[j] * e->qdj[j];
         }
-        tau[j] -= M->joint_damping[j] * e->qdj[j];   /* PyBullet applies MJCF joint damping once per stepSimulation */
+        tau[j] -= M->joint_damping[j] * damp_qd[j];   /* PyBullet applies MJCF joint damping once per stepSimulation */
     }
 }
 
@@ -938,9 +942,11 @@ static void env_step(const struct sso_env* S, env_t* e, const float* a, float* o
                      uint8_t* timeout, float* ep_ret, int32_t* ep_len, int physics) {
     const ss_model* M = &S->M; const ss_params* P = &S->P;
     if (physics == 1) {
-        double tau[NJ];
-        apply_action(M, P, e, a, tau);
+        double tau[NJ], qd0[NJ];
+        memcpy(qd0, e->qdj, sizeof qd0);
+        apply_action(M, P, e, a, tau, qd0);
         for (int s = 0; s < P->n_substeps; s++) {
+            if (P->actuator_mode == 2 && s > 0) apply_action(M, P, e, a, tau, qd0);
             substep(M, P, e, tau);
             if (s < 4) {
                 memcpy(e->trace_q[s], e->pos, 24); memcpy(e->trace_q[s] + 3, e->quat, 32); memcpy(e->trace_q[s] + 7, e->qj, NJ * 8);

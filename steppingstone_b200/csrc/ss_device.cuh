@@ -85,6 +85,7 @@ struct alignas(16) WarpSmem {
     float lim[MAXL][4];       // hinge, dir, penetration
     float dinv[32];
     double parked[4];         // base position (fp64) parked during the substeps
+    float pd[2][32];          // actuator_mode 2: clipped action and the step's joint-damping torque (lane = dof)
     union {
         struct { float H[HS * HS]; float Z[32 * ZS]; } s;
         double d[(HS * HS + 32 * ZS) / 2];

@@ -516,7 +516,9 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     WarpSmem& W = B.W[warp];
     Env E; env_load_phys(S, e, lane, E);
 
-    // robots.py:289-293 apply_action (torque held over the control step) + MJCF joint damping torque
+    // robots.py:289-293 apply_action (torque held over the control step) + MJCF joint damping torque.
+    // actuator_mode 1: the reference's abandoned PD block (robots.py:486-493), once per control step like it;
+    // 2: the same law re-evaluated at every substep ("per-substep PD joint torques", BASELINE north star).
     float tau = 0.f;
     if (lane >= 6 && lane < ND) {
         int j = lane - 6;
@@ -526,7 +528,9 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
             float lo = M.q_lo[j], hi = M.q_hi[j];
             tau = M.pd_p[j] * (x - 2.f * (E.q_dof - 0.5f * (lo + hi)) / (hi - lo)) - M.pd_d[j] * E.v_dof;
         }
-        tau -= M.damping[j] * E.v_dof;
+        const float damp0 = M.damping[j] * E.v_dof;
+        tau -= damp0;
+        if (M.actuator_mode == 2) { W.pd[0][lane] = x; W.pd[1][lane] = damp0; }
     }
     int cflags = -1;
     if (physics) {
@@ -539,6 +543,11 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
 #if SS_SYNC
             __syncthreads();                     // re-align the CTA's warps so that they share instruction fetches
 #endif
+            if (M.actuator_mode == 2 && s > 0 && lane >= 6 && lane < ND) {
+                const int j = lane - 6;
+                const float lo = M.q_lo[j], hi = M.q_hi[j];
+                tau = M.pd_p[j] * (W.pd[0][lane] - 2.f * (E.q_dof - 0.5f * (lo + hi)) / (hi - lo)) - M.pd_d[j] * E.v_dof - W.pd[1][lane];
+            }
             float* dbg = (DIAG && S.dbg && s == M.n_substeps - 1) ? S.dbg + (size_t)e * DBG_FLOATS : nullptr;
             cflags = substep_warp<DIAG>(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg);
             if (DIAG && S.trace_q && s < 4 && !ghost) {

@@ -587,3 +587,28 @@ def test_checkpoint_resume_is_bit_exact(tmp_path):
     sa, sb = a_env.get_state(), b_env.get_state()
     for k in sa:
         assert np.array_equal(sa[k], sb[k]), k
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pd_actuator_modes(mode):
+    """The opt-in PD actuators: the reference's abandoned PD block once per control step (robots.py:486-493, mode 1) and
+    the same law at every substep (the north star's "per-substep PD joint torques", mode 2).  One control step from
+    oracle states; modes 1 and 2 must also differ from each other (the torque really is re-evaluated)."""
+    n = 64
+    prm = dict(actuator_mode=mode)
+    o = make_oracle(0, n, params=prm); g = make_gpu_env(0, n, params=prm)
+    o.reset(); g.reset()
+    st = o.get_state()
+    rng = np.random.RandomState(mode)
+    st["qd"][:, 6:] = rng.randn(n, 21) * 0.3
+    o.set_state(st); g.set_state(st)
+    g.enable_substep_trace(True)
+    a = random_actions(rng, n)
+    o.step(a); g.step(a)
+    qo, qdo = o.substep_trace(); qg, qdg = g.substep_trace()
+    vscale = np.maximum(1.0, np.abs(qdo).max(axis=2))
+    good = (np.abs(qo - qg).max(axis=2)[3] < 2e-4) & ((np.abs(qdo - qdg).max(axis=2) / vscale)[3] < 1e-2)
+    assert good.mean() >= 0.85, "only %.0f%% of envs within tolerance" % (100 * good.mean())
+    if mode == 2:
+        o1 = make_oracle(0, n, params=dict(actuator_mode=1)); o1.reset(); o1.set_state(st); o1.step(a)
+        assert np.abs(o1.substep_trace()[1][3] - qdo[3]).max() > 1e-2

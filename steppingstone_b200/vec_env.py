@@ -233,6 +233,11 @@ class BatchedStepperEnv:
             base = _model.load_tables(self.robot_kind)["tau_max"]
             self._power = float(params_dict["power"])
             self._tables["tau_max"] = base * self._power
+        for ref_name, table in (("P", "pd_p"), ("D", "pd_d")):                  # robots.py:482-483 (PD actuator modes)
+            if ref_name in params_dict:
+                v = np.asarray(params_dict[ref_name], dtype=np.float64)
+                assert v.shape == (ACT_DIM,)
+                self._tables[table] = v
         self._push_tables()
 
     def create_temp_states(self, variant=5):

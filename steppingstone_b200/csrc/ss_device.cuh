@@ -59,7 +59,7 @@ static_assert(sizeof(DevModel) % 16 == 0, "DevModel must be a multiple of 16 byt
 struct DevState {
     double* pos;        // [N][3]   base position (world, double: courses run to x ~ 70 m)
     float* sv;          // [N][64]  0..3 quat xyzw, 4..24 hinge angles, 32..58 generalised velocity (ang3, lin3, hinge21)
-    float* warm;        // [N][32]
+    float* warm;        // [N][SS_NWARM]
     double* terrain;    // [N][n_steps][6]
     double* plank;      // [N][rendered][6]
     double* scal;       // [N][SS_NSCAL]
@@ -70,6 +70,7 @@ struct DevState {
     double* trace_q;    // [4][N][28] or null
     double* trace_qd;   // [4][N][27] or null
     float* dbg;         // [N][DBG_FLOATS] or null
+    int* perm;          // [N] env handled by the k-th warp of the step kernel: envs ordered by their contact count
     int n;
 };
 constexpr int DBG_H = 0, DBG_C = 729, DBG_CAND = 756, DBG_ROWS = 756 + 256, DBG_FLOATS = 756 + 256 + 4 + 32 * 6 + 32 * 32;

@@ -507,7 +507,10 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     const int e_raw = e_begin + blockIdx.x * WARPS_PER_BLOCK + warp;
 #if SS_SYNC
     const bool ghost = e_raw >= e_end;          // keeps hitting the block barriers, stores nothing
-    const int e = ghost ? e_end - 1 : e_raw;
+    // the k-th warp takes the k-th env in order of contact count (sort_envs_kernel): the warps of a CTA then carry
+    // similar solver loads and wait less for each other at the per-substep barrier.  Which warp steps which env has no
+    // effect on the results.
+    const int e = S.perm[ghost ? e_end - 1 : e_raw];
 #else
     if (e_raw >= e_end) return;
     const bool ghost = false;
@@ -758,6 +761,46 @@ __global__ void __launch_bounds__(TS_CELLS) temp_fill_kernel(const DevModel* gm,
     }
 }
 
+// Order the envs of [e_begin, e_end) by the number of contacts they carried in their last substep (the warm-start list),
+// most contacts first (the last, partial wave of the step kernel then gets the light envs): a counting sort with 9 bins.
+//   sort_hist_kernel     key per env + bin totals (block histogram in shared memory, one global atomic per bin and block)
+//   sort_scatter_kernel  perm[base[key] + position] = env; positions from warp-aggregated atomics (the order inside a
+//                        bin is arbitrary -- it only decides which warp steps which env, never a result)
+// bins: int[32] per sort slot, zeroed by a cudaMemsetAsync in front: [0..8] totals, [16..24] cursors.
+constexpr int SORT_THREADS = 256;
+__device__ __forceinline__ int contact_count(const float* wm) {
+    const float4 a = reinterpret_cast<const float4*>(wm)[0], b = reinterpret_cast<const float4*>(wm)[1];
+    return (a.x >= 0.f) + (a.y >= 0.f) + (a.z >= 0.f) + (a.w >= 0.f) + (b.x >= 0.f) + (b.y >= 0.f) + (b.z >= 0.f) + (b.w >= 0.f);
+}
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(DevState S, unsigned char* __restrict__ keys, int* __restrict__ bins,
+                                                                 int e_begin, int e_end) {
+    __shared__ int h[SS_MAX_CONTACTS + 1];
+    if (threadIdx.x <= SS_MAX_CONTACTS) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int e = e_begin + blockIdx.x * SORT_THREADS + threadIdx.x;
+    if (e < e_end) {
+        const int c = contact_count(S.warm + (size_t)e * SS_NWARM);
+        keys[e] = (unsigned char)c;
+        atomicAdd(&h[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x <= SS_MAX_CONTACTS && h[threadIdx.x]) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(DevState S, const unsigned char* __restrict__ keys, int* __restrict__ bins,
+                                                                    int e_begin, int e_end) {
+    const int e = e_begin + blockIdx.x * SORT_THREADS + threadIdx.x, lane = threadIdx.x & 31;
+    const bool live = e < e_end;
+    const int key = live ? keys[e] : SS_MAX_CONTACTS + 1 + lane;          // dead lanes: unique keys, no atomics
+    int base = e_begin;
+    for (int k = SS_MAX_CONTACTS; k > key; k--) base += bins[k];        // heaviest first
+    const unsigned peers = __match_any_sync(FULL, key);
+    const int leader = __ffs(peers) - 1;
+    int start = 0;
+    if (live && lane == leader) start = atomicAdd(&bins[16 + key], __popc(peers));
+    start = __shfl_sync(FULL, start, leader);
+    if (live) S.perm[base + start + __popc(peers & ((1u << lane) - 1u))] = e;
+}
+
 // stand-alone forward-dynamics substep: q [N,28], qd [N,27], tau [N,21] f32 -> q, qd in place (524 B / env-substep)
 __global__ void __launch_bounds__(ABA_BLOCK, SS_ABA_MINB) aba_substep_kernel(const DevModel* gm, float* __restrict__ q, float* __restrict__ qd,
                                                                const float* __restrict__ tau, int n) {
@@ -842,6 +885,7 @@ struct ss_env {
     cudaStream_t pipe[SS_PIPE] = {};
     double host_t[4] = {};           // last ss_step_host: action check, copy+enqueue, waiting on the device, unpacking (seconds)
     float* ts_base = nullptr; double* ts_ctx = nullptr;      // create_temp_states scratch
+    unsigned char* sort_keys = nullptr; int* sort_bins = nullptr;   // sort_envs scratch: [N] keys, SS_PIPE slots of 32 ints
 };
 
 static void fill_model(DevModel& D, const ss_model& m, const ss_params& p) {
@@ -951,6 +995,9 @@ int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t
     CK(cudaMalloc(&S.scal, N * SS_NSCAL * sizeof(double)));
     CK(cudaMalloc(&S.ints, N * SS_NINT * sizeof(int)));
     CK(cudaMalloc(&S.mt, N * 2 * SS_MT_WORDS * sizeof(uint32_t)));
+    CK(cudaMalloc(&S.perm, N * sizeof(int)));
+    CK(cudaMalloc(&E->sort_keys, N)); CK(cudaMalloc(&E->sort_bins, SS_PIPE * 32 * sizeof(int)));
+    { std::vector<int> id(N); for (size_t i = 0; i < N; i++) id[i] = (int)i; CK(cudaMemcpy(S.perm, id.data(), N * sizeof(int), cudaMemcpyHostToDevice)); }
     CK(cudaMalloc(&E->cdf, (size_t)SS_GRID_CELLS * sizeof(double)));
     S.cdf = E->cdf;
     CK(cudaMemset(S.sv, 0, N * 64 * sizeof(float)));
@@ -995,10 +1042,10 @@ void ss_destroy(ss_env* E) {
     cudaDeviceSynchronize();
     DevState& S = E->S;
     cudaFree(E->dm); cudaFree(S.pos); cudaFree(S.sv); cudaFree(S.warm); cudaFree(S.terrain); cudaFree(S.plank);
-    cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.dbg);
+    cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(S.perm); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.dbg);
     cudaFreeHost(E->h_act); cudaFreeHost(E->h_rec); cudaFree(E->d_act); cudaFree(E->d_rec);
     for (int k = 0; k < SS_PIPE; k++) if (E->pipe[k]) cudaStreamDestroy(E->pipe[k]);
-    cudaFree(E->ts_base); cudaFree(E->ts_ctx);
+    cudaFree(E->ts_base); cudaFree(E->ts_ctx); cudaFree(E->sort_keys); cudaFree(E->sort_bins);
     if (E->own) cudaStreamDestroy(E->own);
     delete E;
 }
@@ -1013,8 +1060,16 @@ int ss_reset_all(ss_env* E, float* obs_dev, void* stream) {
 }
 
 static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el,
-                       cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr) {
+                       cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr, int slot = 0) {
     if (e_end < 0) e_end = E->n;
+    if (physics && e_end - e_begin >= 4 * WARPS_PER_BLOCK) {
+        int* bins = E->sort_bins + 32 * slot;
+        const int nb = (e_end - e_begin + SORT_THREADS - 1) / SORT_THREADS;
+        CK(cudaMemsetAsync(bins, 0, 32 * sizeof(int), st));
+        sort_hist_kernel<<<nb, SORT_THREADS, 0, st>>>(E->S, E->sort_keys, bins, e_begin, e_end);
+        sort_scatter_kernel<<<nb, SORT_THREADS, 0, st>>>(E->S, E->sort_keys, bins, e_begin, e_end);
+        E->launches += 2;
+    }
     if (E->S.dbg || E->S.trace_q)
         env_step_kernel<true><<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
                                                                                  e_begin, e_end, packed);
@@ -1084,14 +1139,12 @@ int ss_step_host(ss_env* E, const float* act, float* obs, double* rew, uint8_t* 
         for (size_t i = 0; i < cnt; i++) { uint32_t u = src[i]; dst[i] = u; bad |= (uint32_t)((u & 0x7f800000u) == 0x7f800000u); }
         if (bad) {
             for (int j = 0; j < k; j++) cudaStreamSynchronize(E->pipe[j]);
-            E->launches -= k > 0 ? k - 1 : 0;
             return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
         }
         CK(cudaMemcpyAsync(E->d_act + (size_t)b[k] * NJ, E->h_act + (size_t)b[k] * NJ, n * NJ * 4, cudaMemcpyHostToDevice, st));
-        rc = launch_step(E, E->d_act, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, 1, b[k], b[k + 1], E->d_rec); if (rc) return rc;
+        rc = launch_step(E, E->d_act, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, 1, b[k], b[k + 1], E->d_rec, k); if (rc) return rc;
         CK(cudaMemcpyAsync(E->h_rec + (size_t)b[k] * SS_REC, E->d_rec + (size_t)b[k] * SS_REC, n * SS_REC * 4, cudaMemcpyDeviceToHost, st));
     }
-    E->launches -= nslice - 1;          // one logical kernel launch per step (bench.py's gpu_launches counts steps)
     double t2 = now();
     for (int k = 0; k < nslice; k++) {
         double ta = now();

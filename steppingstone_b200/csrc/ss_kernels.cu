@@ -762,41 +762,47 @@ __global__ void __launch_bounds__(TS_CELLS) temp_fill_kernel(const DevModel* gm,
 }
 
 // Order the envs of [e_begin, e_end) by the number of contacts they carried in their last substep (the warm-start list),
-// most contacts first (the last, partial wave of the step kernel then gets the light envs): a counting sort with 9 bins.
+// envs with a link-link contact first, then most contacts first (the last, partial wave of the step kernel then gets the
+// light envs): a counting sort with 18 bins.
 //   sort_hist_kernel     key per env + bin totals (block histogram in shared memory, one global atomic per bin and block)
 //   sort_scatter_kernel  perm[base[key] + position] = env; positions from warp-aggregated atomics (the order inside a
 //                        bin is arbitrary -- it only decides which warp steps which env, never a result)
-// bins: int[32] per sort slot, zeroed by a cudaMemsetAsync in front: [0..8] totals, [16..24] cursors.
+// bins: int[64] per sort slot, zeroed by a cudaMemsetAsync in front: [0..17] totals, [32..49] cursors.
 constexpr int SORT_THREADS = 256;
-__device__ __forceinline__ int contact_count(const float* wm) {
+constexpr int SORT_BINS = 2 * (SS_MAX_CONTACTS + 1);      // key = contacts + 9 * (one of them is a link-link contact)
+constexpr int SORT_SLOT = 64;                              // ints per sort slot: totals [0..31], cursors [32..63]
+__device__ __forceinline__ int sort_key(const float* wm) {
     const float4 a = reinterpret_cast<const float4*>(wm)[0], b = reinterpret_cast<const float4*>(wm)[1];
-    return (a.x >= 0.f) + (a.y >= 0.f) + (a.z >= 0.f) + (a.w >= 0.f) + (b.x >= 0.f) + (b.y >= 0.f) + (b.z >= 0.f) + (b.w >= 0.f);
+    const int c = (a.x >= 0.f) + (a.y >= 0.f) + (a.z >= 0.f) + (a.w >= 0.f) + (b.x >= 0.f) + (b.y >= 0.f) + (b.z >= 0.f) + (b.w >= 0.f);
+    // link-link contacts (ids >= SS_NGEOM * 8) cost a second substitution pass in the row build: keep those envs together
+    const float m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+    return c + (m >= (float)(SS_NGEOM * 8) ? SS_MAX_CONTACTS + 1 : 0);
 }
 __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(DevState S, unsigned char* __restrict__ keys, int* __restrict__ bins,
                                                                  int e_begin, int e_end) {
-    __shared__ int h[SS_MAX_CONTACTS + 1];
-    if (threadIdx.x <= SS_MAX_CONTACTS) h[threadIdx.x] = 0;
+    __shared__ int h[SORT_BINS];
+    if (threadIdx.x < SORT_BINS) h[threadIdx.x] = 0;
     __syncthreads();
     const int e = e_begin + blockIdx.x * SORT_THREADS + threadIdx.x;
     if (e < e_end) {
-        const int c = contact_count(S.warm + (size_t)e * SS_NWARM);
+        const int c = sort_key(S.warm + (size_t)e * SS_NWARM);
         keys[e] = (unsigned char)c;
         atomicAdd(&h[c], 1);
     }
     __syncthreads();
-    if (threadIdx.x <= SS_MAX_CONTACTS && h[threadIdx.x]) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
+    if (threadIdx.x < SORT_BINS && h[threadIdx.x]) atomicAdd(&bins[threadIdx.x], h[threadIdx.x]);
 }
 __global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(DevState S, const unsigned char* __restrict__ keys, int* __restrict__ bins,
                                                                     int e_begin, int e_end) {
     const int e = e_begin + blockIdx.x * SORT_THREADS + threadIdx.x, lane = threadIdx.x & 31;
     const bool live = e < e_end;
-    const int key = live ? keys[e] : SS_MAX_CONTACTS + 1 + lane;          // dead lanes: unique keys, no atomics
+    const int key = live ? keys[e] : SORT_BINS + lane;                  // dead lanes: unique keys, no atomics
     int base = e_begin;
-    for (int k = SS_MAX_CONTACTS; k > key; k--) base += bins[k];        // heaviest first
+    for (int k = SORT_BINS - 1; k > key; k--) base += bins[k];          // heaviest first
     const unsigned peers = __match_any_sync(FULL, key);
     const int leader = __ffs(peers) - 1;
     int start = 0;
-    if (live && lane == leader) start = atomicAdd(&bins[16 + key], __popc(peers));
+    if (live && lane == leader) start = atomicAdd(&bins[32 + key], __popc(peers));
     start = __shfl_sync(FULL, start, leader);
     if (live) S.perm[base + start + __popc(peers & ((1u << lane) - 1u))] = e;
 }
@@ -996,7 +1002,7 @@ int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t
     CK(cudaMalloc(&S.ints, N * SS_NINT * sizeof(int)));
     CK(cudaMalloc(&S.mt, N * 2 * SS_MT_WORDS * sizeof(uint32_t)));
     CK(cudaMalloc(&S.perm, N * sizeof(int)));
-    CK(cudaMalloc(&E->sort_keys, N)); CK(cudaMalloc(&E->sort_bins, SS_PIPE * 32 * sizeof(int)));
+    CK(cudaMalloc(&E->sort_keys, N)); CK(cudaMalloc(&E->sort_bins, SS_PIPE * SORT_SLOT * sizeof(int)));
     { std::vector<int> id(N); for (size_t i = 0; i < N; i++) id[i] = (int)i; CK(cudaMemcpy(S.perm, id.data(), N * sizeof(int), cudaMemcpyHostToDevice)); }
     CK(cudaMalloc(&E->cdf, (size_t)SS_GRID_CELLS * sizeof(double)));
     S.cdf = E->cdf;
@@ -1063,9 +1069,9 @@ static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint
                        cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr, int slot = 0) {
     if (e_end < 0) e_end = E->n;
     if (physics && e_end - e_begin >= 4 * WARPS_PER_BLOCK) {
-        int* bins = E->sort_bins + 32 * slot;
+        int* bins = E->sort_bins + SORT_SLOT * slot;
         const int nb = (e_end - e_begin + SORT_THREADS - 1) / SORT_THREADS;
-        CK(cudaMemsetAsync(bins, 0, 32 * sizeof(int), st));
+        CK(cudaMemsetAsync(bins, 0, SORT_SLOT * sizeof(int), st));
         sort_hist_kernel<<<nb, SORT_THREADS, 0, st>>>(E->S, E->sort_keys, bins, e_begin, e_end);
         sort_scatter_kernel<<<nb, SORT_THREADS, 0, st>>>(E->S, E->sort_keys, bins, e_begin, e_end);
         E->launches += 2;

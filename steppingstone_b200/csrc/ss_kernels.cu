@@ -59,7 +59,7 @@ struct alignas(16) BlockSmemDyn {
 // TMA bulk copy of the constant tables into shared memory (cp.async.bulk -> UBLKCP) + mbarrier wait
 // ---------------------------------------------------------------------------------------------
 template <typename BS>
-__device__ __forceinline__ void stage_model(BS& B, const DevModel* gm) {
+__device__ __forceinline__ void stage_model_issue(BS& B, const DevModel* gm) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&B.bar);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&B.M);
     if (threadIdx.x == 0) {
@@ -72,11 +72,20 @@ __device__ __forceinline__ void stage_model(BS& B, const DevModel* gm) {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst), "l"(gm), "r"((uint32_t)sizeof(DevModel)), "r"(bar) : "memory");
     }
+}
+template <typename BS>
+__device__ __forceinline__ void stage_model_wait(BS& B) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&B.bar);
     uint32_t ok = 0;
     while (!ok) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
     }
+}
+template <typename BS>
+__device__ __forceinline__ void stage_model(BS& B, const DevModel* gm) {
+    stage_model_issue(B, gm);
+    stage_model_wait(B);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     // results go to one 256-byte record per env -- obs 60 f32, reward, episode return, episode length (int bits),
     // done | timeout << 8 (int bits) -- so that a slice leaves the device in ONE copy.
     BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
-    stage_model(B, gm);
+    stage_model_issue(B, gm);                  // the env's state row is fetched while the tables are in flight
     const DevModel& M = B.M;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e_raw = e_begin + blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -518,6 +527,9 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
 #endif
     WarpSmem& W = B.W[warp];
     Env E; env_load_phys(S, e, lane, E);
+    float a_in = 0.f;
+    if (lane >= 6 && lane < ND) a_in = act[(size_t)e * NJ + lane - 6];
+    stage_model_wait(B);
 
     // robots.py:289-293 apply_action (torque held over the control step) + MJCF joint damping torque.
     // actuator_mode 1: the reference's abandoned PD block (robots.py:486-493), once per control step like it;
@@ -525,7 +537,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     float tau = 0.f;
     if (lane >= 6 && lane < ND) {
         int j = lane - 6;
-        float x = fminf(fmaxf(act[(size_t)e * NJ + j], -1.f), 1.f);
+        float x = fminf(fmaxf(a_in, -1.f), 1.f);
         if (M.actuator_mode == 0) tau = M.tau_max[j] * x;
         else {                                                                     // robots.py:486-493 (opt-in PD)
             float lo = M.q_lo[j], hi = M.q_hi[j];

@@ -1,8 +1,9 @@
 // ss_device.cuh -- warp-per-env device code of the B200 stepping-stone environment (sm_100a).
 //
-// One warp owns one env for a whole control step.  Three lane mappings are used:
+// One warp owns one env for a whole control step.  Four lane mappings are used:
 //   lane = body  (22 bodies)   kinematics, composite inertia, bias forces      -> tree scans with __shfl
 //   lane = dof   (27 dofs)     LDL^T factorisation, velocity / position update
+//   lane = candidate (32 per pass)  collision: (geom, plank, segment end) against the stones, geom pairs against each other
 //   lane = row   (<=32 rows)   constraint rows, Delassus matrix, projected Gauss-Seidel
 // Spatial quantities live in ONE frame per substep: world-aligned axes, origin at the base link's
 // origin ("common frame"), so tree accumulations are plain sums (no per-link spatial transforms).

@@ -99,3 +99,30 @@ def test_mirror_function_matches_the_reference_function():
     assert len(out_a) == len(out_b)
     for x, y in zip(out_a, out_b):
         assert x.shape == y.shape and torch.equal(x, y)
+
+
+def test_sampling_tables_match_the_reference_envs():
+    """curriculum_table / specialist_table / fake_sample_grid against the tables the reference envs build themselves
+    (update_curriculum, update_specialist, fake_*_samples; PyBullet and gym stubbed by tools/fakes)."""
+    from conftest import ROOT
+    from steppingstone_b200 import seeding
+    fakes = os.path.join(ROOT, "tools", "fakes")
+    sys.path.insert(0, REF); sys.path.insert(0, fakes)
+    try:
+        import pybullet as fake
+        from mocca_envs.mike import MikeStepperEnv
+        from mocca_envs.walker3d_envs import Walker3DStepperEnv
+        for cls in (MikeStepperEnv, Walker3DStepperEnv):
+            fake.reset_world()
+            env = cls()
+            for c in range(0, 7):
+                env.update_curriculum(c)
+                assert np.array_equal(env.yaw_pitch_r_tilt_prob, seeding.curriculum_table(c)), (cls.__name__, "curriculum", c)
+            for s in range(0, 6):
+                env.update_specialist(s)
+                assert np.array_equal(env.yaw_pitch_r_tilt_prob, seeding.specialist_table(s)), (cls.__name__, "specialist", s)
+            grid = seeding.fake_sample_grid()
+            for k, name in enumerate(("fake_yaw_samples", "fake_pitch_samples", "fake_r_samples", "fake_x_tilt_samples", "fake_y_tilt_samples")):
+                assert np.array_equal(getattr(env, name), grid[k]), name
+    finally:
+        sys.path.remove(REF); sys.path.remove(fakes)

@@ -126,3 +126,32 @@ def test_sampling_tables_match_the_reference_envs():
                 assert np.array_equal(getattr(env, name), grid[k]), name
     finally:
         sys.path.remove(REF); sys.path.remove(fakes)
+
+
+def test_mirror_indices_and_registry_match_the_reference():
+    """get_mirror_indices() of the reference envs themselves, and the gym registration (ids, max_episode_steps)."""
+    from conftest import ROOT
+    from steppingstone_b200 import mirror, model
+    fakes = os.path.join(ROOT, "tools", "fakes")
+    sys.path.insert(0, REF); sys.path.insert(0, fakes)
+    try:
+        import pybullet as fake
+        from mocca_envs.mike import MikeStepperEnv
+        from mocca_envs.walker3d_envs import Walker3DStepperEnv
+        ours = mirror.get_mirror_indices()
+        for cls in (Walker3DStepperEnv, MikeStepperEnv):
+            fake.reset_world()
+            env = cls()
+            theirs = env.get_mirror_indices()
+            assert len(theirs) == 6
+            for a, b in zip(ours, theirs):
+                assert np.array_equal(np.asarray(a), np.asarray(b)), cls.__name__
+            assert env.observation_space.shape == (60,) and env.action_space.shape == (21,)
+        src = open(os.path.join(REF, ".environments", "mocca_envs", "__init__.py")).read()
+        for env_id, kind in (("Walker3DStepperEnv-v0", 0), ("MikeStepperEnv-v0", 1)):
+            block = src[src.index('id="%s"' % env_id):]
+            block = block[:block.index(")")]
+            assert "max_episode_steps=1000" in block.replace(" ", "")
+            assert model.make_params(kind).max_episode_steps == 1000
+    finally:
+        sys.path.remove(REF); sys.path.remove(fakes)

@@ -155,3 +155,34 @@ def test_mirror_indices_and_registry_match_the_reference():
             assert model.make_params(kind).max_episode_steps == 1000
     finally:
         sys.path.remove(REF); sys.path.remove(fakes)
+
+
+def test_robot_tables_match_the_reference_robot_classes():
+    """Joint order, joint limits, torque limits, start pose and base height as the reference's Walker3D / Mike robot classes
+    hold them after load_robot_model + calc_torque_limits + reset (robots.py:371-431, 385-388, 446-468, 535-545, 581-618)."""
+    from conftest import ROOT
+    from steppingstone_b200 import model
+    fakes = os.path.join(ROOT, "tools", "fakes")
+    sys.path.insert(0, REF); sys.path.insert(0, fakes)
+    try:
+        import pybullet as fake
+        from mocca_envs.mike import MikeStepperEnv
+        from mocca_envs.walker3d_envs import Walker3DStepperEnv
+        for kind, cls in ((0, Walker3DStepperEnv), (1, MikeStepperEnv)):
+            fake.reset_world()
+            env = cls()
+            env.seed(8)
+            T = model.load_tables(kind)
+            joints = env.robot.ordered_joints
+            assert [j.joint_name for j in joints] == model.JOINT_NAMES
+            assert np.allclose([j.lowerLimit for j in joints], T["q_lo"], atol=1e-12)
+            assert np.allclose([j.upperLimit for j in joints], T["q_hi"], atol=1e-12)
+            assert np.allclose(env.robot.torque_limits, T["tau_max"])
+            env.reset()
+            q = np.array([j.get_state()[0] for j in joints])
+            mirrored = getattr(env.robot, "mirrored", False)
+            if not mirrored:
+                assert np.allclose(q, T["init_q"], atol=1e-12)
+            assert np.allclose(env.robot.body_xyz, T["init_pos"], atol=1e-9)
+    finally:
+        sys.path.remove(REF); sys.path.remove(fakes)

@@ -955,7 +955,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                     a = fmaf(z[4 * j], v.x, a); a = fmaf(z[4 * j + 1], v.y, a); a = fmaf(z[4 * j + 2], v.z, a);
                     if (4 * j + 3 < ND) a = fmaf(z[4 * j + 3], v.w, a);
                 }
-                a4[jj] = a * invD - (sl == r && rtype >= 0 ? omc : 0.f);
+                a4[jj] = a * invD - (sl == r && rtype >= 0 ? (rtype == 1 ? -cfmt : omc) : 0.f);
             }
             switch (g) {
                 case 0: Ar[0] = a4[0]; Ar[1] = a4[1]; Ar[2] = a4[2]; Ar[3] = a4[3]; break;
@@ -999,6 +999,15 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
             lam = (lane == (RR)) ? sum_ : lam;                                 \
             c = fmaf(-Ar[(RR)], dl_, c);                                       \
         }
+        // contact normals (lo = 0, hi = "infinity") keep e = c - lam instead of c: the impulse change is max(e, -lam),
+        // one FMNMX and no subtraction on the dependent chain; their diagonal coefficient carries +cfm instead of -(1 - cfm)
+#define SS_NORMAL_STEP(RR)                                                     \
+        {                                                                      \
+            float d_ = fmaxf(c, -lam);                                         \
+            float dl_ = shfl(d_, (RR));                                        \
+            lam = (lane == (RR)) ? lam + d_ : lam;                             \
+            c = fmaf(-Ar[(RR)], dl_, c);                                       \
+        }
         // warm start: fold the cached normal impulses in (dv = sum_s W_s lam_s)
 #pragma unroll
         for (int k = 0; k < MAXC; k += 2)
@@ -1018,7 +1027,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
             }
 #pragma unroll
             for (int k = 0; k < MAXC; k += 2)
-                if (nc > k) { SS_ROW_STEP(k); SS_ROW_STEP(k + 1); }
+                if (nc > k) { SS_NORMAL_STEP(k); SS_NORMAL_STEP(k + 1); }
             float ln = shfl(lam, nsrc);
             if (isfric) { bool live = ln > 0.f; hi_c = live ? mu * ln : lam; lo_c = live ? -hi_c : lam; }
 #pragma unroll
@@ -1028,6 +1037,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 }
         }
 #undef SS_ROW_STEP
+#undef SS_NORMAL_STEP
         if (DIAG && dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
         // ---- velocity update: dv = L^-T sum_r w_r lam_r ----
         __syncwarp();        // the w rows written above (lane = row) are read below with lane = dof

@@ -20,6 +20,9 @@ import time
 
 import numpy as np
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -168,10 +171,14 @@ def run_b200(args, wl):
     acts = torch.clamp(torch.randn(ring, N, 21, device=dev, generator=gen) * 0.22, -1, 1).contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    sampler = ClockSampler(local); sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 5.0:     # nvidia-smi needs ~1 s to print its first sample
+        time.sleep(0.02)
+    sampler.rows.clear()
     for i in range(W):
         env.step(acts[i % ring])
     barrier()
-    sampler = ClockSampler(local); sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     l0 = env.launch_count
     done_count = torch.zeros((), dtype=torch.int64, device=dev)

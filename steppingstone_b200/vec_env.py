@@ -185,7 +185,12 @@ class BatchedStepperEnv:
         stack [N, ...] of identical tables.  Accepted table shapes: the env's 5-D grid [11,11,11,11,11]
         (yaw, pitch, r, x_tilt, y_tilt), and the 2-D [11,11] / 3-D [11,11,11] tables train.py:267-271, 311-315 build
         (``update_sample_prob_1/_2``, walker3d_envs.py:1307-1315): those are embedded at index 0 of the missing axes --
-        every r / tilt sample of the stepper envs is the same value (mike.py:74-76), so this is the draw they mean."""
+        every r / tilt sample of the stepper envs is the same value (mike.py:74-76), so this is the draw they mean.
+
+        Difference from the reference: there each env keeps its own table and takes a new one ONLY if it advanced a stone
+        in its last step (``if self.update_terrain:``, mike.py:828) -- envs that did not keep sampling from their old
+        table.  Here the one shared table is replaced for every env; the immediate re-sample of the next-next stone
+        happens, as in the reference, only for the envs whose ``update_terrain`` flag is set."""
         p = expand_sample_table(probs, self.num_envs)
         self._set_table(p, apply_now=True)
 

@@ -39,7 +39,7 @@ def seeding_restore(kind):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 10
+    assert len(GOLDEN) >= 11
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -62,12 +62,17 @@ def test_env_logic_matches_reference(path):
     T = len(g["rew"])
     n_ep = 0
     ts_step = list(g["ts_step"]) if "ts_step" in g.files else []
+    sp_step = list(g["sp_step"]) if "sp_step" in g.files else []
     for t in range(T):
         ob, rew, done, to, er, el = o.step_injected(g["actions"][t][None], g["q"][t][None], g["qd"][t][None], g["contact"][t][None])
         assert bool(done[0]) == bool(g["done"][t]), "done differs at step %d" % t
         assert bool(to[0]) == bool(g["bad"][t]), "bad_transition differs at step %d" % t
         assert abs(float(rew[0]) - g["rew"][t]) < 1e-5 * max(1.0, abs(g["rew"][t])), "reward differs at step %d: ref %r oracle %r" % (t, g["rew"][t], rew[0])
         close(ob[0], g["obs"][t], "obs", t)
+        if t in sp_step:
+            # update_sample_prob (mike.py:827-830): new table, immediate re-sample iff this step advanced a stone
+            from steppingstone_b200 import seeding
+            o.set_sample_cdf(seeding.choice_cdf(g["sp_tables"][sp_step.index(t)].astype(np.float64)), apply_now=True)
         if t in ts_step:
             # value-guided sampling probes (create_temp_states_1/_2/create_temp_states, mike.py:699-753): the
             # reference leaves walk_target at the last grid cell, so the NEXT step's reward checks that too

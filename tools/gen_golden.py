@@ -16,7 +16,9 @@ reproduce these outputs; the GPU path is then checked against the oracle (tests/
 
 Tapes: (A) oracle-simulated random-action rollouts (falls, resets, RNG continuity); (B) a kinematic "ghost
 walker" that dwells on each stone (stone advances, step bonus, plank ring buffer, curriculum sampler, time-limit
-truncation); (C) the same with stop_frames=5 and no time limit, to reach the last stone (target bonus, index clamp).
+truncation); (C) the same with stop_frames=5 and no time limit, to reach the last stone (target bonus, index clamp);
+(D) ghost tapes that call create_temp_states_1/_2/create_temp_states after every stone advance; (E) a Mike ghost tape that
+calls update_sample_prob with a fresh sparse 11^5 table after stone advances (immediate re-sample + later draws).
 """
 import os
 import sys
@@ -119,7 +121,7 @@ class RefWorker:
 
 
 def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=None, curriculum=None, oracle_params=None,
-           temp_states=False):
+           temp_states=False, sample_prob_every=0):
     """tape_fn(t, worker, sim) -> (q, qd, contact) for step t.  temp_states: after every step that advanced a stone
     call the reference's create_temp_states_1 / _2 / create_temp_states (value-guided sampling probes) and record them."""
     fk = make_oracle(kind, seed)
@@ -130,6 +132,7 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
     terr = [w.env.terrain_info.copy()]; terr_at = [-1]
     Q, QD, C, OBS, REW, DONE, BAD, EPR, EPL, NXT, CNT, POT = ([] for _ in range(12))
     ts_step, ts_variant, ts_data = [], [], {}
+    sp_rng = np.random.RandomState(4242 + seed); sp_step, sp_tables = [], []
     for t in range(T):
         q, qd, c = tape_fn(t, w)
         ob, r, d, info, (nxt, cnt, pot) = w.step(actions[t], q, qd, c)
@@ -138,6 +141,15 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
         EPR.append(info["episode"]["r"] if "episode" in info else 0.0)
         EPL.append(info["episode"]["l"] if "episode" in info else 0)
         NXT.append(nxt); CNT.append(cnt); POT.append(pot)
+        if sample_prob_every and not d and w.env.update_terrain and (nxt % sample_prob_every) != 0:
+            # update_sample_prob (mike.py:827-830 through envs_utils.py:568-571) right after a step that advanced a stone
+            # (the only moment the reference env takes the table): new sampling table + immediate re-sample of the
+            # next-next stone.  Skipped on every third stone so that draws from a table set earlier are covered too.
+            table = sp_rng.rand(11, 11, 11, 11, 11) * (sp_rng.rand(11, 11, 11, 11, 11) < 0.02)
+            table[5, 5, 0, 5, 5] += 1e-3
+            table = table.astype(np.float32).astype(np.float64)          # stored as float32 in the fixture: keep it exact
+            w.env.update_sample_prob(table.copy())
+            sp_step.append(t); sp_tables.append(table)
         if temp_states and not d and w.env.update_terrain:
             k = len(ts_step)
             variant = 5 if k == 2 else (2 if k % 4 == 1 and k < 10 else 1)
@@ -156,6 +168,8 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
                ep_r=np.array(EPR), ep_l=np.array(EPL, np.int32), next_step=np.array(NXT, np.int32),
                reached_count=np.array(CNT, np.int32), potential=np.array(POT),
                terrain=np.array(terr), terrain_at=np.array(terr_at, np.int32))
+    if sample_prob_every:
+        rec.update(sp_step=np.array(sp_step, np.int32), sp_tables=np.array(sp_tables, np.float32))
     if temp_states:
         e = w.env
         rec.update(ts_step=np.array(ts_step, np.int32), ts_variant=np.array(ts_variant, np.int32),
@@ -233,6 +247,12 @@ def main():
         acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)
         record("%s_ghost_laststone" % nm, kind, 12, acts, ghost_tape(kind, 12, rng, 6), T, time_limit=None,
                env_params={"stop_frames": 5}, curriculum=(3 if kind == 1 else None))
+        if kind == 1:
+            T = 160
+            rng = np.random.RandomState(66)
+            acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)
+            record("mike_ghost_sampleprob", kind, 14, acts, ghost_tape(kind, 14, rng, 6), T, time_limit=None,
+                   env_params={"stop_frames": 5}, curriculum=5, sample_prob_every=3)
         T = 150
         rng = np.random.RandomState(55 + kind)
         acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)

@@ -1123,8 +1123,18 @@ __device__ __forceinline__ void mt_doubles_warp(uint32_t* mt, int& pos, double* 
     pos = mt_doubles_impl(mt, pos, out, count, lane);
 }
 __device__ __forceinline__ double mt_one_double_warp(uint32_t* mt, int& pos, double* scratch, int lane) {
+    if (pos <= SS_MT_N - 2) {              // both words lie in the current block: every lane computes the draw in registers
+        const double u = mt_make_double(mt_temper(mt[pos]), mt_temper(mt[pos + 1]));
+        pos += 2;
+        return u;
+    }
+    // the draw straddles (or follows) a twist: the general routine through the scratch buffer.  The value is read back
+    // through a volatile pointer after a warp barrier: a plain read of scratch[0] here was once satisfied with a stale
+    // value left by an earlier launch (resample_kernel re-drew the previous uniform; tests/test_gpu_parity.py::
+    // test_update_sample_prob_resamples_flagged_envs).
     mt_doubles_warp(mt, pos, scratch, 1, lane);
-    return scratch[0];
+    __syncwarp();
+    return reinterpret_cast<volatile double*>(scratch)[0];
 }
 
 // pybullet.getEulerFromQuaternion

@@ -612,3 +612,35 @@ def test_pd_actuator_modes(mode):
     if mode == 2:
         o1 = make_oracle(0, n, params=dict(actuator_mode=1)); o1.reset(); o1.set_state(st); o1.step(a)
         assert np.abs(o1.substep_trace()[1][3] - qdo[3]).max() > 1e-2
+
+
+def test_update_sample_prob_resamples_flagged_envs():
+    """update_sample_prob (mike.py:827-830): a fresh sparse table; envs that advanced a stone in their last step re-draw
+    the next-next stone at once (resample_kernel), the others only at their next advance -- terrain, planks and RNG
+    streams against the oracle (fp64 on both sides)."""
+    from steppingstone_b200 import seeding
+    n = 40
+    o = make_oracle(1, n); g = make_gpu_env(1, n)
+    o.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(5))); g.update_curriculum(5)
+    o.reset(); g.reset()
+    st = o.get_state()
+    _force_advance(st, n, 29)
+    st["ints"][::2, 1] = 3                       # every other env does not advance: no immediate re-sample there
+    o.set_state(st); g.set_state(st)
+    a = np.zeros((n, 21), np.float32)
+    o.env_post(a); g.env_post(a)
+    rng = np.random.RandomState(12)
+    table = (rng.rand(11, 11, 11, 11, 11) * (rng.rand(11, 11, 11, 11, 11) < 0.02)).astype(np.float32).astype(np.float64)
+    table[5, 5, 0, 5, 5] += 1e-3
+    before = o.get_state()["terrain"].copy()
+    o.set_sample_cdf(seeding.choice_cdf(table), apply_now=True); g.update_sample_prob(table)
+    so, sg = o.get_state(), g.get_state()
+    changed = np.abs(so["terrain"] - before).max(axis=(1, 2)) > 0
+    assert changed[1::2].all() and not changed[::2].any()
+    assert np.array_equal(so["mt"], sg["mt"]) and np.array_equal(so["ints"], sg["ints"])
+    assert _maxerr(so["terrain"], sg["terrain"]) < 1e-9 and _maxerr(so["plank"], sg["plank"]) < 1e-9
+    # a later advance of the other envs draws from the new table on both sides
+    st = o.get_state(); _force_advance(st, n, 29); o.set_state(st); g.set_state(st)
+    o.env_post(a); g.env_post(a)
+    so, sg = o.get_state(), g.get_state()
+    assert np.array_equal(so["mt"], sg["mt"]) and _maxerr(so["terrain"], sg["terrain"]) < 1e-9

@@ -48,49 +48,113 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons of ONE GPU sampled DURING the timed region.  NVML in-process (a query is
+    ~0.1 ms, so even the 0.1 s timed region of a short run holds tens of samples); an `nvidia-smi -lms` child
+    process is the fallback when the NVML binding is missing (its first sample alone takes ~1 s)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None, period_s=0.004):
+        self.index, self.uuid, self.period = index, uuid, period_s
+        self.rows, self.proc, self.thread = [], None, None       # rows: (sm_mhz, sm_max_mhz, set(reasons))
+        self.source, self._nv, self._h, self._mx = None, None, None, None
+        self._run = threading.Event()
 
-    def start(self):
+    # ---- NVML ----
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u if isinstance(u, bytes) else u.encode()); break
+                except Exception:
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(u); break
+                    except Exception:
+                        h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self._mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)   # fail here, not in the thread
+        self._nv, self._h = pynvml, h
+
+    def _nvml_sample(self):
+        nv, h = self._nv, self._h
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
         except Exception:
-            self.proc = None
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        return sm, self._mx, {n for n, b in self.BITS.items() if mask & b}
 
-    def _read(self):
+    def _nvml_loop(self):
+        while self._run.is_set():
+            try:
+                self.rows.append(self._nvml_sample())
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    # ---- nvidia-smi fallback ----
+    def _smi_loop(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             if len(r) < 6:
                 continue
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                self.rows.append((float(r[0]), float(r[1]),
+                                  {n for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for n, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def start(self):
+        try:
+            self._nvml_open()
+            self.source = "nvml"
+            self._run.set()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self._nv = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid and ("GPU-" + self.uuid) or str(self.index),
+                                          "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self.thread.start()
+            t_wait = time.perf_counter()
+            while not self.rows and time.perf_counter() - t_wait < 8.0:   # its first sample takes ~1 s
+                time.sleep(0.02)
+        except Exception:
+            self.proc = None
+
+    def mark(self):
+        """Forget the samples taken so far (call right before the timed region)."""
+        self.rows.clear()
+
+    def stop(self):
+        if self._nv is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"], "samples": 0}
+        self._run.clear()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        rows = list(self.rows)
+        sm = [r[0] for r in rows]
+        reasons = set().union(*[r[2] for r in rows]) if rows else set()
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[1] for r in rows) if rows else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, seed=8):
@@ -171,11 +235,12 @@ def run_b200(args, wl):
     acts = torch.clamp(torch.randn(ring, N, 21, device=dev, generator=gen) * 0.22, -1, 1).contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    sampler = ClockSampler(local); sampler.start()
-    t_wait = time.perf_counter()
-    while not sampler.rows and time.perf_counter() - t_wait < 5.0:     # nvidia-smi needs ~1 s to print its first sample
-        time.sleep(0.02)
-    sampler.rows.clear()
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)   # CUDA_VISIBLE_DEVICES may renumber the GPUs
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid); sampler.start()
+    sampler.mark()
     for i in range(W):
         env.step(acts[i % ring])
     barrier()
@@ -183,6 +248,8 @@ def run_b200(args, wl):
     l0 = env.launch_count
     done_count = torch.zeros((), dtype=torch.int64, device=dev)
     barrier()
+    if sampler.source == "nvml":
+        sampler.mark()                             # NVML: samples of the timed region only (the fallback keeps the warm-up's too)
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xff)                      # L2 flush between timed steps (outside the event pair)
@@ -193,6 +260,13 @@ def run_b200(args, wl):
     t_wall = time.perf_counter() - t_wall0
     launches = env.launch_count - l0
     clocks = sampler.stop()
+    if world > 1:                                  # every rank samples its own GPU; rank 0 reports the slowest + all reasons
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        med = [c["sm_mhz"] for c in allc]
+        clocks = dict(clocks, per_rank_sm_mhz=med, reasons=sorted(set().union(*[set(c["reasons"]) for c in allc])))
+        if all(m is not None for m in med):
+            clocks["sm_mhz"] = min(med)
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     t_dev = float(step_ms.sum()) * 1e-3
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)

@@ -11,7 +11,8 @@
  *     published algorithm: link-frame Featherstone ABA as in btMultiBody::
  *     computeAccelerationsArticulatedBodyAlgorithmMultiDof, unit-impulse responses as in
  *     calcAccelerationDeltasMultiDof, rows and PGS as in btMultiBodyConstraintSolver).  PARITY UNPINNED
- *     against PyBullet for this last part.
+ *     against PyBullet for this last part (per substep; behaviourally pinned by the reference's shipped
+ *     policies, tests/test_policy_behaviour.py).
  *
  * The GPU library computes the same quantities by a different route (world-frame composite-rigid-body
  * inertia + LDL^T, Delassus-space PGS) in fp32, so agreement between the two is a real check.

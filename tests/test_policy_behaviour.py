@@ -7,7 +7,7 @@ model, the collision set or the actuation differ (the negative controls below sh
 1000-step episode -- 33 is the ceiling, a stone needs 30 dwell frames (walker3d_envs.py:984-990) -- is evidence that
 the restated Bullet arithmetic is close to the real one.  It is a behavioural check, not a per-substep one: DESIGN.md 5.
 
-Fixtures: tests/golden/policy_{w3d,w3d_base,mike}.npz -- the actors' weights, read from the checkpoints as DATA by
+Fixtures: tests/golden/policies/{w3d_latest,w3d_base,mike_latest}.npz -- the actors' weights, read from the checkpoints as DATA by
 tools/read_legacy_checkpoint.py (an allow-list pickle walker; nothing the files name is imported or executed).
 Forward pass: common/controller.py SoftsignActor.forward (:193-201), deterministic action = the mean (Policy.act
 with deterministic=True, :104-110), exactly what playground/enjoy.py runs.
@@ -19,13 +19,13 @@ import pytest
 
 from conftest import make_gpu_env, make_oracle
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policies")
 
 # (fixture, robot kind, terrain_mode, curriculum level or None)
 CASES = {
-    "w3d_latest_shipped_terrain": ("policy_w3d.npz", 0, None, None),        # +-30 deg up/down, walker3d_envs.py:723-730
-    "w3d_base_flat_stage": ("policy_w3d_base.npz", 0, 2, None),             # BASELINE configs[1]: the flat-terrain stage
-    "mike_latest_curriculum5": ("policy_mike.npz", 1, None, 5),             # BASELINE configs[2]: yaw +-20, pitch +-50
+    "w3d_latest_shipped_terrain": ("w3d_latest.npz", 0, None, None),        # +-30 deg up/down, walker3d_envs.py:723-730
+    "w3d_base_flat_stage": ("w3d_base.npz", 0, 2, None),             # BASELINE configs[1]: the flat-terrain stage
+    "mike_latest_curriculum5": ("mike_latest.npz", 1, None, 5),             # BASELINE configs[2]: yaw +-20, pitch +-50
 }
 RETURN_BAR = 2500.0     # reference bar: 1000 (train.py:503); measured here: 3350-4300
 STONES_BAR = 20.0       # measured: 28.9-33.0 stones in the first episode
@@ -90,7 +90,7 @@ def test_policy_is_a_sensitive_probe(override):
     (the reference loads it with URDF_USE_SELF_COLLISION, robots.py:496-500) or when the stones' contact damping
     (bullet_objects.py:67) is ten times smaller -- so the pass above says something about the physics."""
     o = make_oracle(0, 8, params=override)
-    ret, length, stones = first_episodes_oracle(o, load_actor("policy_w3d.npz"), 600)
+    ret, length, stones = first_episodes_oracle(o, load_actor("w3d_latest.npz"), 600)
     o.close()
     assert ret.mean() < 1000.0 and stones.mean() < 10.0, (ret, stones)
 

@@ -12,7 +12,7 @@ Legacy layout (torch/serialization.py, ``_legacy_load``): pickle(magic) pickle(p
 storages by persistent id ('storage', type, key, location, numel, view)) pickle([storage keys]) then, per key, an int64
 element count followed by the raw little-endian elements.
 
-    python tools/read_legacy_checkpoint.py            # writes tests/golden/policy_{w3d,w3d_base,mike}.npz
+    python tools/read_legacy_checkpoint.py            # writes tests/golden/policies/{w3d_latest,w3d_base,mike_latest}.npz
 """
 import collections
 import io
@@ -141,15 +141,15 @@ def actor_arrays(path):
 
 
 def main():
-    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    os.makedirs(os.path.join(ROOT, "tests", "golden", "policies"), exist_ok=True)
     # Walker3DStepperEnv-v0_best.pt holds the same weights as _latest.pt (checked array by array): not stored twice
-    for tag, fname in (("w3d", "mocca_envs:Walker3DStepperEnv-v0_latest.pt"), ("w3d_base", "mocca_envs:Walker3DStepperEnv-v0_base.pt"),
-                       ("mike", "mocca_envs:MikeStepperEnv-v0_latest.pt")):
+    for tag, fname in (("w3d_latest", "mocca_envs:Walker3DStepperEnv-v0_latest.pt"), ("w3d_base", "mocca_envs:Walker3DStepperEnv-v0_base.pt"),
+                       ("mike_latest", "mocca_envs:MikeStepperEnv-v0_latest.pt")):
         arrs = actor_arrays(os.path.join(MODELS, fname))
         print(tag, str(arrs["actor_class"]), {k: v.shape for k, v in arrs.items() if k.endswith("_w")}, "logstd", arrs["logstd"][:3])
         if "--dry" in sys.argv:
             continue
-        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "policy_%s.npz" % tag), source=np.array(fname), **arrs)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "policies", "%s.npz" % tag), source=np.array(fname), **arrs)
 
 
 if __name__ == "__main__":

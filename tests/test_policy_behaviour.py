@@ -138,3 +138,44 @@ def test_shipped_policy_walks_the_stones_on_the_gpu(case):
     assert ret.mean() > RETURN_BAR, (ret.mean(), np.sort(ret)[:8])
     assert (ret > 1000.0).mean() > 0.9, np.sort(ret)[:16]
     assert length.mean() > 800, length.mean()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["w3d_latest_shipped_terrain", "mike_latest_curriculum5"])
+def test_per_substep_parity_on_walking_states(case):
+    """PER-SUBSTEP GPU <-> oracle parity on the states that matter: snapshots of the shipped policy WALKING the stones
+    in the oracle (feet loaded on tilted stones, swing-leg self-contacts, hinges on their limits), instead of the
+    random-action tumbling of tests/test_gpu_parity.py.  From each snapshot, four 1/240 s substeps, each teacher-forced
+    from the oracle's state, under the policy's action.  Same fp32 tolerances as test_teacher_forced_substeps:
+    1e-3 of the env's velocity scale on generalised velocities, 5e-6 on generalised positions."""
+    name, kind, terrain_mode, curriculum = CASES[case]
+    from steppingstone_b200 import seeding
+    n = 32
+    P = load_actor(name)
+    walker = make_oracle(kind, n, terrain_mode=terrain_mode)
+    if curriculum is not None:
+        walker.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(curriculum)))
+    prm = dict(n_substeps=1)
+    o = make_oracle(kind, n, params=prm, terrain_mode=terrain_mode)
+    g = make_gpu_env(kind, n, params=prm, terrain_mode=terrain_mode)
+    o.reset(); g.reset(); g.enable_substep_trace(True)
+    obs = walker.reset()
+    worst_v = worst_q = 0.0
+    n_contacts = 0
+    for t in range(1, 521):
+        a = actor_numpy(P, obs)
+        if t in (40, 130, 250, 380, 520):
+            o.set_state(walker.get_state())
+            for s in range(4):
+                st = o.get_state(); g.set_state(st)
+                n_contacts += int((st["warm"][:, :8] >= 0).sum())
+                o.step(a); g.step(a)
+                qo, qdo = o.substep_trace(); qg, qdg = g.substep_trace()
+                vscale = np.maximum(1.0, np.abs(qdo[0]).max(axis=1, keepdims=True))
+                worst_v = max(worst_v, float(np.max(np.abs(qdo[0] - qdg[0]) / vscale)))
+                worst_q = max(worst_q, float(np.max(np.abs(qo[0] - qg[0]))))
+        obs = walker.step(a)[0]
+    print("%s: walking-state substeps: max dv (relative) %.2e, max dq %.2e, %d cached contacts seen" % (case, worst_v, worst_q, n_contacts))
+    walker.close(); o.close(); g.close()
+    assert n_contacts > 100, "the snapshots should be in contact with the stones"
+    assert worst_v < 1e-3 and worst_q < 5e-6

@@ -261,12 +261,15 @@ def run_b200(args, wl):
     launches = env.launch_count - l0
     clocks = sampler.stop()
     if world > 1:                                  # every rank samples its own GPU; rank 0 reports the slowest + all reasons
-        allc = [None] * world
-        dist.all_gather_object(allc, clocks)
-        med = [c["sm_mhz"] for c in allc]
-        clocks = dict(clocks, per_rank_sm_mhz=med, reasons=sorted(set().union(*[set(c["reasons"]) for c in allc])))
-        if all(m is not None for m in med):
-            clocks["sm_mhz"] = min(med)
+        names = ClockSampler.NAMES
+        cmin = torch.tensor([clocks["sm_mhz"] if clocks["sm_mhz"] is not None else float("inf")], dtype=torch.float64, device=dev)
+        flags = torch.tensor([1.0 if n_ in clocks["reasons"] else 0.0 for n_ in names], dtype=torch.float64, device=dev)
+        dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        other = [r_ for r_ in clocks["reasons"] if r_ not in names]
+        clocks = dict(clocks, reasons=sorted(other + [n_ for n_, f_ in zip(names, flags.tolist()) if f_ > 0]),
+                      sm_mhz_rank0=clocks["sm_mhz"], ranks=world)
+        clocks["sm_mhz"] = None if cmin.item() == float("inf") else float(cmin.item())
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     t_dev = float(step_ms.sum()) * 1e-3
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)

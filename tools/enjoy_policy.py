@@ -51,18 +51,25 @@ def main():
         obs = env.reset()
         ret = torch.zeros(n, device=env.device); length = torch.zeros(n, dtype=torch.int32, device=env.device)
         open_ = torch.ones(n, dtype=torch.bool, device=env.device)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for t in range(args.steps):
-            obs, rew, done, info = env.step(actor(obs))
+            a = actor(obs)
+            ev[t][0].record()
+            obs, rew, done, info = env.step(a)
+            ev[t][1].record()
             fin = open_ & (done != 0)
             ret = torch.where(fin, info.episode_r, ret); length = torch.where(fin, info.episode_l, length)
             open_ = open_ & ~fin
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         fin = (~open_).cpu().numpy(); r = ret.cpu().numpy()[fin]; l = length.cpu().numpy()[fin]
+        ms = np.array([a_.elapsed_time(b_) for a_, b_ in ev])          # env.step alone (sort kernels + env_step_kernel), L2 warm
+        walk = ms[min(200, args.steps // 2):]
         out.append({"policy": tag, "env": label, "envs": n, "steps": args.steps, "first_episodes_finished": int(fin.sum()),
                     "return_mean": float(r.mean()), "return_median": float(np.median(r)), "return_p05": float(np.percentile(r, 5)),
                     "frac_above_reference_bar_1000": float((r > 1000).mean()), "length_mean": float(l.mean()),
-                    "env_steps_per_s_policy_in_loop": n * args.steps / dt})
+                    "env_steps_per_s_policy_in_loop": n * args.steps / dt,
+                    "env_step_ms_on_walking_states": float(walk.mean()), "env_steps_per_s_device_on_walking_states": n / (float(walk.mean()) * 1e-3)})
         env.close()
     print(json.dumps(out, indent=1))
 

@@ -20,8 +20,27 @@ import time
 
 import numpy as np
 
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout and nothing else may: libraries write there too (NCCL prints its
+    "NCCL version ..." banner on stdout at NCCL_DEBUG=VERSION/WARN/INFO).  Keep a private duplicate of the real stdout
+    for the result line and point file descriptor 1 -- Python's sys.stdout and every C library alike -- at stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    fd = 1 if _RESULT_FD is None else _RESULT_FD
+    while data:
+        data = data[os.write(fd, data):]
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -201,7 +220,7 @@ def run_reference(args, wl):
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args, wl):
@@ -413,7 +432,7 @@ def run_b200(args, wl):
             line["roofline_temp_states"] = tsf
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     env.close()
     if world > 1:
         dist.destroy_process_group()
@@ -433,6 +452,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     wl = WORKLOADS[args.workload]
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, wl)
     else:

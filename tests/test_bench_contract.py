@@ -38,3 +38,15 @@ def test_reference_arm_other_ranks_stay_silent():
 def test_b200_arm_fails_loudly_without_a_gpu():
     res = _run(["--gpus", "1", "--steps", "3", "--warmup", "3"])
     assert res.returncode != 0 and "no CUDA device" in (res.stderr + res.stdout)
+
+
+def test_stdout_carries_only_the_result_line():
+    """Libraries write to stdout too (NCCL prints "NCCL version ..." there at NCCL_DEBUG=VERSION/WARN, seen in a
+    2-GPU torchrun of this bench): after claim_stdout() anything written to fd 1 -- from Python or from C -- lands on
+    stderr and only emit() reaches the real stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('chatter'); bench.emit({'a': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert "NCCL version" in r.stderr and "chatter" in r.stderr

@@ -39,7 +39,7 @@ def seeding_restore(kind):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 11
+    assert len(GOLDEN) >= 13
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

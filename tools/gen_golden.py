@@ -18,7 +18,9 @@ Tapes: (A) oracle-simulated random-action rollouts (falls, resets, RNG continuit
 walker" that dwells on each stone (stone advances, step bonus, plank ring buffer, curriculum sampler, time-limit
 truncation); (C) the same with stop_frames=5 and no time limit, to reach the last stone (target bonus, index clamp);
 (D) ghost tapes that call create_temp_states_1/_2/create_temp_states after every stone advance; (E) a Mike ghost tape that
-calls update_sample_prob with a fresh sparse 11^5 table after stone advances (immediate re-sample + later draws).
+calls update_sample_prob with a fresh sparse 11^5 table after stone advances (immediate re-sample + later draws);
+(F) the reference's shipped policies walking the stones in the oracle's simulation (closed loop), replayed through the
+reference env: stone advances by physical foot contact, step bonuses and progress rewards on realistic gaits.
 """
 import os
 import sys
@@ -181,9 +183,11 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
         name, T, int(np.sum(DONE)), int(np.max(NXT)), np.min(REW), np.max(REW)))
 
 
-def simulated_tape(kind, seed, actions, T):
+def simulated_tape(kind, seed, actions, T, curriculum=None):
     """(A) post-physics states from the oracle's own simulation (normal mode)."""
     sim = make_oracle(kind, seed)
+    if curriculum is not None:
+        sim.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(curriculum)))
     sim.reset()
 
     def fn(t, w):
@@ -192,6 +196,27 @@ def simulated_tape(kind, seed, actions, T):
         st = sim.get_state()
         return q[3, 0].copy(), qd[3, 0].copy(), st["scalars"][0, 14:16].copy()
     return fn
+
+
+def policy_actions(kind, seed, T, fixture, curriculum=None):
+    """(F) action tape of a shipped reference policy (tests/golden/policies/*.npz, tools/read_legacy_checkpoint.py)
+    walking the stones closed-loop in the oracle: common/controller.py SoftsignActor.forward, deterministic."""
+    z = np.load(os.path.join(OUT, "policies", fixture))
+    sim = make_oracle(kind, seed)
+    if curriculum is not None:
+        sim.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(curriculum)))
+    obs = sim.reset()
+    softsign = lambda x: x / (1.0 + np.abs(x))
+    acts = []
+    for t in range(T):
+        x = softsign(obs @ z["fc1_w"].T + z["fc1_b"]); x = softsign(x @ z["fc2_w"].T + z["fc2_b"])
+        x = softsign(x @ z["fc3_w"].T + z["fc3_b"])
+        x = np.maximum(x @ z["fc4_w"].T + z["fc4_b"], 0.0); x = np.maximum(x @ z["fc5_w"].T + z["fc5_b"], 0.0)
+        a = np.tanh(x @ z["out_w"].T + z["out_b"]).astype(np.float32)
+        acts.append(a[0])
+        obs = sim.step(a)[0]
+    sim.close()
+    return np.array(acts, np.float32)
 
 
 def ghost_tape(kind, seed, rng, dwell):
@@ -253,6 +278,11 @@ def main():
             acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)
             record("mike_ghost_sampleprob", kind, 14, acts, ghost_tape(kind, 14, rng, 6), T, time_limit=None,
                    env_params={"stop_frames": 5}, curriculum=5, sample_prob_every=3)
+        # (F) the shipped policy walking: stone advances by physical foot contact, step bonuses, progress rewards
+        T = 420
+        cur = 5 if kind == 1 else None
+        acts = policy_actions(kind, 8, T, "w3d_latest.npz" if kind == 0 else "mike_latest.npz", cur)
+        record("%s_walk_policy" % nm, kind, 8, acts, simulated_tape(kind, 8, acts, T, cur), T, curriculum=cur)
         T = 150
         rng = np.random.RandomState(55 + kind)
         acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)

@@ -8,6 +8,10 @@ log-std -1.5, 256-wide MLPs) and algorithms/ppo.py:40-108 (hyper-parameters of t
 they are callers of the hot path, not part of it.
 
     python examples/train_ppo.py --env mocca_envs:Walker3DStepperEnv-v0 --envs 4096 --steps 16 --iters 150
+    torchrun --nproc-per-node 8 examples/train_ppo.py --envs 8192 ...      # data parallel: env shards stay local,
+                                                                           # global advantage stats + gradient all-reduce
+    python examples/train_ppo.py --init-actor tests/golden/policies/mike_latest.npz --critic-warmup 20 --logstd -2.5 \
+        --env mocca_envs:MikeStepperEnv-v0 --curriculum 5                   # fine-tune a policy the reference ships
 
 Prints one line per iteration: finished-episode mean return / length (Monitor statistics) and env-steps/s.
 """
@@ -20,7 +24,7 @@ import torch
 import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from steppingstone_b200 import make_vec_envs                      # noqa: E402
+from steppingstone_b200 import make_vec_envs, sharding            # noqa: E402
 from steppingstone_b200.collector import EpisodeStats, collect_rollout   # noqa: E402
 from steppingstone_b200.storage import RolloutStorage             # noqa: E402
 
@@ -35,14 +39,43 @@ def mlp(sizes, act, gain):
     return nn.Sequential(*layers)
 
 
-class ActorCritic(nn.Module):
-    """Policy.act / get_value / evaluate_actions (common/controller.py:106-150)."""
+class SoftsignActor(nn.Module):
+    """common/controller.py:165-201: fc1-fc3 softsign, fc4-fc5 relu, ``out`` (tanh applied by the caller here) -- the
+    architecture of the policies the reference ships, so that their weights load (``--init-actor``)."""
 
     def __init__(self, obs_dim, act_dim, h=256):
         super().__init__()
-        self.actor = mlp([obs_dim, h, h, h, act_dim], nn.ReLU, nn.init.calculate_gain("relu"))
+        self.fc1, self.fc2, self.fc3 = nn.Linear(obs_dim, h), nn.Linear(h, h), nn.Linear(h, h)
+        self.fc4, self.fc5, self.out = nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, act_dim)
+
+    def forward(self, x):
+        f = nn.functional
+        x = f.softsign(self.fc1(x)); x = f.softsign(self.fc2(x)); x = f.softsign(self.fc3(x))
+        x = f.relu(self.fc4(x)); x = f.relu(self.fc5(x))
+        return self.out(x)
+
+    def load_npz(self, path):
+        """Weights as extracted by tools/read_legacy_checkpoint.py (tests/golden/policies/*.npz)."""
+        import numpy as np
+        z = np.load(path)
+        with torch.no_grad():
+            for name in ("fc1", "fc2", "fc3", "fc4", "fc5", "out"):
+                lin = getattr(self, name)
+                lin.weight.copy_(torch.as_tensor(z[name + "_w"])); lin.bias.copy_(torch.as_tensor(z[name + "_b"]))
+
+
+class ActorCritic(nn.Module):
+    """Policy.act / get_value / evaluate_actions (common/controller.py:106-150).  ``arch="reference"``: the shipped
+    policies' SoftsignActor; ``"small"``: a 3-hidden-layer ReLU actor (faster, the default of the earlier logs)."""
+
+    def __init__(self, obs_dim, act_dim, h=256, arch="small", logstd=-1.5):
+        super().__init__()
+        if arch == "reference":
+            self.actor = SoftsignActor(obs_dim, act_dim, h)
+        else:
+            self.actor = mlp([obs_dim, h, h, h, act_dim], nn.ReLU, nn.init.calculate_gain("relu"))
         self.critic = mlp([obs_dim, h, h, h, h, 1], nn.ReLU, nn.init.calculate_gain("relu"))
-        self.logstd = nn.Parameter(torch.full((act_dim,), -1.5))          # DiagGaussian(noise=-1.5), controller.py:21
+        self.logstd = nn.Parameter(torch.full((act_dim,), float(logstd)))  # DiagGaussian(noise=-1.5), controller.py:21
 
     def dist(self, obs):
         return torch.distributions.Normal(torch.tanh(self.actor(obs)), self.logstd.exp())
@@ -60,10 +93,16 @@ class ActorCritic(nn.Module):
         return self.critic(obs), d.log_prob(action).sum(-1, keepdim=True), d.entropy().sum(-1).mean(), states
 
 
-def ppo_update(ac, opt, rollouts, epochs, num_mini_batch, clip=0.2, max_grad_norm=2.0):
-    """algorithms/ppo.py:40-108 (use_clipped_value_loss=False, entropy_coef 0, value_loss_coef 1)."""
+def ppo_update(ac, opt, rollouts, epochs, num_mini_batch, clip=0.2, max_grad_norm=2.0, distributed=False, actor_frozen=False):
+    """algorithms/ppo.py:40-108 (use_clipped_value_loss=False, entropy_coef 0, value_loss_coef 1).  ``distributed``:
+    every rank holds its own rollout shard (steppingstone_b200/sharding.py): the advantages are normalised with the
+    GLOBAL mean / std and the gradients averaged over the ranks -- the update of the gathered batch without moving it."""
     adv = rollouts.returns[:-1] - rollouts.value_preds[:-1]
-    adv = (adv - adv.mean()) / (adv.std() + 1e-5)
+    if distributed:
+        mean, std = sharding.global_advantage_stats(adv)
+        adv = (adv - mean) / (std + 1e-5)
+    else:
+        adv = (adv - adv.mean()) / (adv.std() + 1e-5)
     vl = al = 0.0
     for _ in range(epochs):
         for obs, states, actions, _, returns, masks, old_logp, adv_t in rollouts.feed_forward_generator(adv, num_mini_batch):
@@ -72,7 +111,9 @@ def ppo_update(ac, opt, rollouts, epochs, num_mini_batch, clip=0.2, max_grad_nor
             action_loss = -torch.min(ratio * adv_t, torch.clamp(ratio, 1 - clip, 1 + clip) * adv_t).mean()
             value_loss = 0.5 * (returns - values).pow(2).mean()
             opt.zero_grad(set_to_none=True)
-            (value_loss + action_loss).backward()
+            (value_loss + (0.0 if actor_frozen else 1.0) * action_loss).backward()
+            if distributed:
+                sharding.allreduce_gradients(list(ac.parameters()))
             nn.utils.clip_grad_norm_(ac.parameters(), max_grad_norm)
             opt.step()
             vl += value_loss.detach(); al += action_loss.detach()
@@ -96,13 +137,37 @@ def main():
     ap.add_argument("--lr-decay", type=float, default=0.99, help="per 40000 frames, floor 3e-5 (train.py:215-216)")
     ap.add_argument("--terrain-mode", type=int, default=None)
     ap.add_argument("--minutes", type=float, default=0.0, help="stop after this many minutes (0 = run all iterations)")
+    ap.add_argument("--arch", default="small", choices=["small", "reference"],
+                    help="reference = common/controller.py SoftsignActor, the architecture of the shipped policies")
+    ap.add_argument("--init-actor", default=None,
+                    help="start from a shipped policy's weights (tests/golden/policies/*.npz; implies --arch reference)")
+    ap.add_argument("--critic-warmup", type=int, default=0,
+                    help="iterations that train the critic only (use with --init-actor: the critic starts random)")
+    ap.add_argument("--logstd", type=float, default=-1.5, help="initial log-std of the Gaussian policy (controller.py:21)")
     args = ap.parse_args()
-    torch.manual_seed(args.seed)
-    dev = torch.device("cuda", 0)
-    envs = make_vec_envs(args.env, args.seed, args.envs, output="torch", device=0, terrain_mode=args.terrain_mode)
+    # one process per GPU under torchrun: --envs is PER GPU (weak scaling, like bench.py); rank r owns the global env
+    # indices [r * envs, (r + 1) * envs) with the reference's seed + index numbering (sharding.py)
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    distributed = world > 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if distributed:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(args.seed + rank)
+    if distributed:
+        envs = sharding.make_sharded_vec_envs(args.env, args.seed, args.envs * world, rank, world, output="torch",
+                                              device=local, terrain_mode=args.terrain_mode)
+    else:
+        envs = make_vec_envs(args.env, args.seed, args.envs, output="torch", device=local, terrain_mode=args.terrain_mode)
     if "Mike" in args.env:
         envs.update_curriculum(args.curriculum)
-    ac = ActorCritic(60, 21).to(dev)
+    if args.init_actor:
+        args.arch = "reference"
+    ac = ActorCritic(60, 21, arch=args.arch, logstd=args.logstd).to(dev)
+    if args.init_actor:
+        ac.actor.load_npz(args.init_actor)
+    if distributed:
+        sharding.broadcast_parameters(ac)
     opt = torch.optim.Adam(ac.parameters(), lr=args.lr, eps=1e-5)
     rollouts = RolloutStorage(args.steps, args.envs, (60,), 21, 1, device=dev)
     rollouts.observations[0].copy_(envs.reset())
@@ -120,24 +185,32 @@ def main():
             next_value = ac.get_value(rollouts.observations[-1], None, None)
         rollouts.compute_returns(next_value, True, 0.99, 0.95)
         torch.cuda.synchronize(); t1 = time.time()
-        vl, al = ppo_update(ac, opt, rollouts, args.epochs, num_mini_batch)
+        vl, al = ppo_update(ac, opt, rollouts, args.epochs, num_mini_batch, distributed=distributed,
+                            actor_frozen=it < args.critic_warmup)
         rollouts.after_update()
         torch.cuda.synchronize(); t2 = time.time()
-        frames += args.envs * args.steps
-        mean_r, n_ep = stats.mean()
-        mean_l = float(stats.len_sum.item()) / max(n_ep, 1)
+        frames += args.envs * args.steps * world
+        if distributed:                             # global finished-episode statistics drive the curriculum trigger
+            mean_r, n_ep = sharding.reduce_episode_stats(stats.sum, stats.count)
+            mean_l, _ = sharding.reduce_episode_stats(stats.len_sum, stats.count)
+        else:
+            mean_r, n_ep = stats.mean()
+            mean_l = float(stats.len_sum.item()) / max(n_ep, 1)
         # stones reached per 1000 env-steps: a step carrying the step bonus (50 exp(-d/0.25), walker3d_envs.py:1001-1006)
         stones = float((rollouts.rewards > 10.0).sum().item()) / (args.envs * args.steps) * 1000.0
-        print("iter %4d frames %9d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  stones/1000steps %5.2f  value_loss %8.3f  "
-              "curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy)  update %.2fs" % (
-                  it, frames, n_ep, mean_r, mean_l, float(rollouts.rewards.mean()), stones, vl, curriculum, lr,
-                  args.envs * args.steps / (t1 - t0), t2 - t1), flush=True)
+        if rank == 0:
+            print("iter %4d frames %9d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  stones/1000steps %5.2f  value_loss %8.3f  "
+                  "curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy, %d GPU)  update %.2fs" % (
+                      it, frames, n_ep, mean_r, mean_l, float(rollouts.rewards.mean()), stones, vl, curriculum, lr,
+                      world * args.envs * args.steps / (t1 - t0), world, t2 - t1), flush=True)
         if args.use_curriculum and n_ep > 0 and mean_r > 1000 and curriculum <= 4:      # train.py:503-506
             curriculum += 1
             envs.update_curriculum(curriculum)
         if args.minutes and time.time() - t_start > args.minutes * 60:
             break
     envs.close()
+    if distributed:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -71,3 +71,26 @@ def broadcast_table(table, src=0, group=None):
     """Curriculum / sampling tables are decided on rank 0 and broadcast (train.py:118, 269-271)."""
     dist.broadcast(table, src=src, group=group)
     return table
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Every rank starts from rank ``src``'s policy (the reference has ONE actor_critic, train.py:150-176)."""
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def allreduce_gradients(parameters, group=None):
+    """Average the gradients over the ranks with ONE all-reduce of a flat buffer (~0.5 M parameters = 2 MB for the
+    reference's 256-wide actor + critic): with equal shards and per-rank mean losses this is the gradient of the mean
+    loss over the global minibatch, i.e. what ``algorithms/ppo.py:60-104`` computes on the gathered rollout."""
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

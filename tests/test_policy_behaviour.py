@@ -179,3 +179,19 @@ def test_per_substep_parity_on_walking_states(case):
     walker.close(); o.close(); g.close()
     assert n_contacts > 100, "the snapshots should be in contact with the stones"
     assert worst_v < 1e-3 and worst_q < 5e-6
+
+
+def test_example_actor_loads_the_shipped_weights():
+    """examples/train_ppo.py's SoftsignActor (``--init-actor``) reproduces the numpy forward pass of this file."""
+    import importlib.util
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_ppo_actor", os.path.join(root, "examples", "train_ppo.py"))
+    tp = importlib.util.module_from_spec(spec); sys.modules["train_ppo_actor"] = tp; spec.loader.exec_module(tp)
+    ac = tp.ActorCritic(60, 21, arch="reference")
+    ac.actor.load_npz(os.path.join(GOLD, "mike_latest.npz"))
+    obs = np.random.RandomState(0).randn(32, 60).astype(np.float32)
+    with torch.no_grad():
+        a = ac.dist(torch.as_tensor(obs)).mean.numpy()
+    assert np.abs(a - actor_numpy(load_actor("mike_latest.npz"), obs)).max() < 1e-5

@@ -29,9 +29,13 @@ def claim_stdout():
     for the result line and point file descriptor 1 -- Python's sys.stdout and every C library alike -- at stderr."""
     global _RESULT_FD
     if _RESULT_FD is None:
-        sys.stdout.flush()
-        _RESULT_FD = os.dup(1)
-        os.dup2(2, 1)
+        try:
+            sys.stdout.flush()
+            fd = os.dup(1)
+            os.dup2(2, 1)
+            _RESULT_FD = fd
+        except OSError:                # no usable stderr: leave stdout as it is rather than fail the run
+            _RESULT_FD = None
 
 
 def emit(line):

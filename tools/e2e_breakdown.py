@@ -1,8 +1,8 @@
 """Where the end-to-end (host buffers) step time goes.  Run on the GPU box: python tools/e2e_breakdown.py"""
-import os, sys, time, ctypes
+import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from steppingstone_b200 import BatchedStepperEnv, native
+from steppingstone_b200 import BatchedStepperEnv
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 env = BatchedStepperEnv("mocca_envs:Walker3DStepperEnv-v0", 8, N, terrain_mode=2)

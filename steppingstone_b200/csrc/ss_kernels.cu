@@ -977,6 +977,8 @@ static int configure_kernels(size_t smem) {
     return 0;
 }
 
+static int create_device_state(ss_env* E, const ss_model* model, const uint32_t* mt_env, const uint32_t* mt_aux);
+
 extern "C" {
 
 const char* ss_last_error(void) { return g_err.c_str(); }
@@ -999,7 +1001,22 @@ int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t
     fill_model(E->hm, *model, *params);
     E->smem = sizeof(BlockSmem);
     int rc = configure_kernels(E->smem);
-    if (rc) { delete E; return rc; }
+    if (!rc) rc = create_device_state(E, model, mt_env, mt_aux);
+    if (rc) {                                    // e.g. out of memory half-way: release what was allocated, keep the message
+        const std::string msg = g_err;
+        ss_destroy(E);
+        cudaGetLastError();
+        g_err = msg;
+        return rc;
+    }
+    *out = E;
+    return SS_OK;
+}
+
+} // extern "C"
+
+static int create_device_state(ss_env* E, const ss_model* model, const uint32_t* mt_env, const uint32_t* mt_aux) {
+    const int n = E->n;
     DevState& S = E->S;
     S.n = n; S.n_cells = SS_GRID_CELLS;
     size_t N = (size_t)n;
@@ -1050,9 +1067,10 @@ int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t
         CK(cudaMemcpy(S.pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice));
     }
     CK(cudaStreamCreateWithFlags(&E->own, cudaStreamNonBlocking));
-    *out = E;
     return SS_OK;
 }
+
+extern "C" {
 
 void ss_destroy(ss_env* E) {
     if (!E) return;

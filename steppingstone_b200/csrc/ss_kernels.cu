@@ -58,6 +58,15 @@ struct alignas(16) BlockSmemDyn {
 // ---------------------------------------------------------------------------------------------
 // TMA bulk copy of the constant tables into shared memory (cp.async.bulk -> UBLKCP) + mbarrier wait
 // ---------------------------------------------------------------------------------------------
+#ifdef SS_SIMT_EMU   // tests/simt_emu builds this file for the host (test infrastructure): the bulk copy is a memcpy
+template <typename BS>
+__device__ __forceinline__ void stage_model_issue(BS& B, const DevModel* gm) {
+    if (threadIdx.x == 0) memcpy(&B.M, gm, sizeof(DevModel));
+    __syncthreads();
+}
+template <typename BS>
+__device__ __forceinline__ void stage_model_wait(BS&) {}
+#else
 template <typename BS>
 __device__ __forceinline__ void stage_model_issue(BS& B, const DevModel* gm) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&B.bar);
@@ -82,6 +91,7 @@ __device__ __forceinline__ void stage_model_wait(BS& B) {
                      : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
     }
 }
+#endif
 template <typename BS>
 __device__ __forceinline__ void stage_model(BS& B, const DevModel* gm) {
     stage_model_issue(B, gm);

@@ -1,0 +1,86 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of tests/simt_emu/_build/libss_emu.so -- the product's CUDA sources compiled
+for the host on the SIMT emulation of this directory (cuda_runtime.h, emu_runtime.cpp, build_emu.py).
+
+``EmuEnv`` has the shape of ``oracle.binding.Oracle`` (reset / step / get_state / set_state / substep_trace) so that the
+parity tests read the same.  Nothing under steppingstone_b200/ imports this; the struct definitions and the C-ABI
+signature table are the product's (steppingstone_b200.model / native), the library is not.
+"""
+import ctypes
+
+import numpy as np
+
+from steppingstone_b200 import model, native, seeding
+
+from . import build_emu
+
+OBS, NJ = 60, 21
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(build_emu.build())
+        for name, (res, args) in native._SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class EmuEnv:
+    def __init__(self, kind, n, seed=8, params=None, terrain_mode=None):
+        self.lib = load()
+        self.n = n
+        self.model = model.make_model(kind)
+        self.params = model.make_params(kind, params, terrain_mode)
+        self.n_steps, self.rendered = self.params.n_steps, self.params.rendered
+        mt_env = seeding.env_streams(seed, 0, n); mt_aux = seeding.aux_streams(kind, seed, 0, n)
+        self.h = ctypes.c_void_p()
+        rc = self.lib.ss_create(ctypes.byref(self.model), ctypes.byref(self.params), n, 0, mt_env.ctypes.data, mt_aux.ctypes.data,
+                                ctypes.byref(self.h))
+        assert rc == 0, self.lib.ss_last_error()
+        self._timeout = np.zeros(n, np.uint8); self._ep_ret = np.zeros(n, np.float32); self._ep_len = np.zeros(n, np.int32)
+
+    def _ck(self, rc, what):
+        assert rc == 0, "%s: %s" % (what, self.lib.ss_last_error())
+
+    def close(self):
+        if self.h:
+            self.lib.ss_destroy(self.h); self.h = ctypes.c_void_p()
+
+    def set_sample_cdf(self, cdf, apply_now=False):
+        cdf = np.ascontiguousarray(cdf, dtype=np.float64)
+        self._ck(self.lib.ss_set_sample_cdf(self.h, cdf.ctypes.data, cdf.size, int(apply_now), None), "ss_set_sample_cdf")
+
+    def reset(self):
+        obs = np.zeros((self.n, OBS), np.float32)
+        self._ck(self.lib.ss_reset_host(self.h, obs.ctypes.data), "ss_reset_host")
+        return obs
+
+    def step(self, act):
+        a = np.ascontiguousarray(act, dtype=np.float32)
+        assert a.shape == (self.n, NJ)
+        obs = np.zeros((self.n, OBS), np.float32); rew = np.zeros(self.n, np.float64); done = np.zeros(self.n, np.bool_)
+        self._ck(self.lib.ss_step_host(self.h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                                       self._timeout.ctypes.data, self._ep_ret.ctypes.data, self._ep_len.ctypes.data), "ss_step_host")
+        return obs, rew, done, self._timeout.copy(), self._ep_ret.copy(), self._ep_len.copy()
+
+    def get_state(self):
+        st = native.alloc_state(self.n, self.n_steps, self.rendered)
+        v = native.make_view(st)
+        self._ck(self.lib.ss_get_state(self.h, ctypes.byref(v)), "ss_get_state")
+        return st
+
+    def set_state(self, st):
+        st = {k: (None if a is None else np.ascontiguousarray(a)) for k, a in st.items()}
+        v = native.make_view(st)
+        self._ck(self.lib.ss_set_state(self.h, ctypes.byref(v)), "ss_set_state")
+
+    def enable_substep_trace(self, on=True):
+        self._ck(self.lib.ss_enable_substep_trace(self.h, int(on)), "ss_enable_substep_trace")
+
+    def substep_trace(self):
+        q = np.zeros((4, self.n, native.NQ)); qd = np.zeros((4, self.n, native.ND))
+        self._ck(self.lib.ss_substep_trace(self.h, q.ctypes.data, qd.ctypes.data), "ss_substep_trace")
+        return q, qd

@@ -1,0 +1,111 @@
+"""CPU: the PRODUCT's CUDA sources (steppingstone_b200/csrc/ss_kernels.cu + ss_device.cuh), compiled for the host on the
+SIMT emulation of tests/simt_emu/ (one fiber per CUDA thread, warp collectives as rendez-vous), against the oracle.
+
+This is test infrastructure: it checks the kernels' arithmetic and warp-level data flow in the CPU suite (where no GPU
+exists) and lets a kernel change be verified before it is timed on a B200.  It is not a CPU path of the product -- the
+package cannot load this library, and the `-m gpu` tests remain the parity tests proper (same comparisons, real device).
+Differences from the device: libm sqrt/sincos/exp instead of the GPU's approximations, no FMA contraction of a*b+c;
+both are far below the fp32-vs-fp64 tolerances used here (the same as in tests/test_gpu_parity.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_oracle, random_actions
+from simt_emu.binding import EmuEnv
+
+KINDS = [0, 1]
+
+
+def _maxerr(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_emulated_kernels_reset_parity(kind):
+    """env_reset_kernel: terrain generator on the env's MT19937 stream (bit-exact), planks, bookkeeping, observation."""
+    n = 6
+    o = make_oracle(kind, n); g = EmuEnv(kind, n)
+    obs_o = o.reset(); obs_g = g.reset()
+    so, sg = o.get_state(), g.get_state()
+    assert np.array_equal(so["mt"], sg["mt"])
+    assert np.array_equal(so["ints"], sg["ints"])
+    assert _maxerr(so["terrain"], sg["terrain"]) < 1e-9
+    assert _maxerr(so["plank"], sg["plank"]) < 1e-9
+    assert _maxerr(so["q"], sg["q"]) < 1e-6
+    assert _maxerr(obs_o, obs_g) < 1e-5
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("k_steps", [0, 12])
+def test_emulated_kernels_teacher_forced_substeps(kind, k_steps):
+    """env_step_kernel, per substep (dynamics + collision + rows + 20 PGS iterations + integration) from the oracle's
+    state: the comparison and tolerances of tests/test_gpu_parity.py::test_teacher_forced_substeps."""
+    n = 8
+    prm = dict(n_substeps=1)
+    o = make_oracle(kind, n, params=prm); g = EmuEnv(kind, n, params=prm)
+    o.reset(); g.reset()
+    rng0 = np.random.RandomState(k_steps)
+    for _ in range(4 * k_steps):
+        o.step(random_actions(rng0, n))
+    g.enable_substep_trace(True)
+    rng = np.random.RandomState(100 + k_steps)
+    worst_v = worst_q = 0.0
+    for s in range(6):
+        a = random_actions(rng, n)
+        st = o.get_state(); g.set_state(st)
+        o.step(a); g.step(a)
+        qo, qdo = o.substep_trace(); qg, qdg = g.substep_trace()
+        vscale = np.maximum(1.0, np.abs(qdo[0]).max(axis=1, keepdims=True))
+        worst_v = max(worst_v, float(np.max(np.abs(qdo[0] - qdg[0]) / vscale))); worst_q = max(worst_q, _maxerr(qo[0], qg[0]))
+    o.close(); g.close()
+    assert worst_v < 1e-3 and worst_q < 5e-6, (worst_v, worst_q)
+
+
+@pytest.mark.parametrize("case", ["w3d_latest_shipped_terrain", "mike_latest_curriculum5"])
+def test_emulated_kernels_on_walking_states(case):
+    """Per-substep parity on snapshots of a shipped policy walking the stones (feet loaded, self-contacts, hinges on
+    limits) -- the CPU twin of tests/test_policy_behaviour.py::test_per_substep_parity_on_walking_states."""
+    from steppingstone_b200 import seeding
+    from test_policy_behaviour import CASES, actor_numpy, load_actor
+    name, kind, terrain_mode, curriculum = CASES[case]
+    n = 8
+    P = load_actor(name)
+    walker = make_oracle(kind, n, terrain_mode=terrain_mode)
+    if curriculum is not None:
+        walker.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(curriculum)))
+    prm = dict(n_substeps=1)
+    o = make_oracle(kind, n, params=prm, terrain_mode=terrain_mode)
+    g = EmuEnv(kind, n, params=prm, terrain_mode=terrain_mode)
+    o.reset(); g.reset(); g.enable_substep_trace(True)
+    obs = walker.reset()
+    worst_v = worst_q = 0.0
+    n_contacts = 0
+    for t in range(1, 251):
+        a = actor_numpy(P, obs)
+        if t in (40, 130, 250):
+            o.set_state(walker.get_state())
+            for s in range(4):
+                st = o.get_state(); g.set_state(st)
+                n_contacts += int((st["warm"][:, :8] >= 0).sum())
+                o.step(a); g.step(a)
+                qo, qdo = o.substep_trace(); qg, qdg = g.substep_trace()
+                vscale = np.maximum(1.0, np.abs(qdo[0]).max(axis=1, keepdims=True))
+                worst_v = max(worst_v, float(np.max(np.abs(qdo[0] - qdg[0]) / vscale)))
+                worst_q = max(worst_q, _maxerr(qo[0], qg[0]))
+        obs = walker.step(a)[0]
+    walker.close(); o.close(); g.close()
+    assert n_contacts > 50
+    assert worst_v < 1e-3 and worst_q < 5e-6, (worst_v, worst_q)
+
+
+def test_emulation_is_not_reachable_from_the_product():
+    """The emulated library lives under tests/ and has its own binding: the package never names it."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "steppingstone_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "libss_emu" not in src and "simt_emu.binding" not in src and "import simt_emu" not in src, f

@@ -84,3 +84,33 @@ class EmuEnv:
         q = np.zeros((4, self.n, native.NQ)); qd = np.zeros((4, self.n, native.ND))
         self._ck(self.lib.ss_substep_trace(self.h, q.ctypes.data, qd.ctypes.data), "ss_substep_trace")
         return q, qd
+
+    # ---- the other kernels (host arrays stand in for device buffers) ----
+    def env_post(self, act):
+        a = np.ascontiguousarray(act, dtype=np.float32)
+        obs = np.zeros((self.n, OBS), np.float32); rew = np.zeros(self.n, np.float32); done = np.zeros(self.n, np.uint8)
+        self._ck(self.lib.ss_env_post(self.h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, None), "ss_env_post")
+        return obs, rew, done
+
+    def aba_substep(self, q, qd, tau):
+        q = np.ascontiguousarray(q, dtype=np.float32).copy(); qd = np.ascontiguousarray(qd, dtype=np.float32).copy()
+        tau = np.ascontiguousarray(tau, dtype=np.float32)
+        self._ck(self.lib.ss_aba_substep(self.h, q.ctypes.data, qd.ctypes.data, tau.ctypes.data, q.shape[0], None), "ss_aba_substep")
+        return q, qd
+
+    def create_temp_states(self, variant, grid, restore=None):
+        G = int(self.lib.ss_temp_state_cells(int(variant)))
+        out = np.zeros((self.n, G, OBS), np.float32)
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        r = None if restore is None else np.ascontiguousarray(restore, dtype=np.float64)
+        self._ck(self.lib.ss_create_temp_states(self.h, int(variant), grid.ctypes.data, None if r is None else r.ctypes.data,
+                                                out.ctypes.data, None), "ss_create_temp_states")
+        return out
+
+    def gae(self, rewards, value_preds, masks, bad_masks, gamma, lam):
+        T, N = rewards.shape
+        f = [np.ascontiguousarray(a, dtype=np.float32) for a in (rewards, value_preds, masks, bad_masks)]
+        ret = np.zeros((T + 1, N), np.float32)
+        self._ck(self.lib.ss_gae(f[0].ctypes.data, f[1].ctypes.data, f[2].ctypes.data, f[3].ctypes.data, ret.ctypes.data, T, N,
+                                 float(gamma), float(lam), None), "ss_gae")
+        return ret

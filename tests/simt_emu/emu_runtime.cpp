@@ -5,6 +5,10 @@ namespace simt {
 
 Block* g_block = nullptr;
 unsigned char* g_dynsmem = nullptr;
+// 0: lanes are resumed in ascending order within every scheduling round, 1: descending, 2: a fixed pseudo-random
+// permutation per round.  A kernel whose threads only communicate across collectives / barriers gives bit-identical
+// results under every order; one that relies on lock-step execution does not (a poor man's racecheck).
+static int g_order = 0;
 static const size_t STACK = 512 * 1024;
 
 static void fiber_exit_bookkeeping(Block* b, Fiber* f) {
@@ -51,8 +55,13 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                     makecontext(&f.ctx, trampoline, 0);
                 }
                 long rounds = 0;
+                uint32_t lcg = 12345u;
                 while (b.live > 0) {
-                    for (int t = 0; t < nthreads; t++) {
+                    if (g_order == 2) lcg = lcg * 1664525u + 1013904223u;
+                    const int off = g_order == 2 ? (int)((lcg >> 8) % (uint32_t)nthreads) : 0;
+                    const int stride = g_order == 2 ? 1 + 2 * (int)((lcg >> 20) % 8u) : 1;     // odd stride: a permutation when nthreads is a power of two
+                    for (int i = 0; i < nthreads; i++) {
+                        int t = g_order == 1 ? nthreads - 1 - i : (g_order == 2 && (nthreads & (nthreads - 1)) == 0 ? (off + i * stride) & (nthreads - 1) : i);
                         Fiber& f = b.fibers[t];
                         if (f.done) continue;
                         b.cur = &f;
@@ -65,3 +74,5 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 }
 
 }  // namespace simt
+
+extern "C" void simt_emu_set_order(int order) { simt::g_order = order; }

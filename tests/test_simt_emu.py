@@ -109,3 +109,98 @@ def test_emulation_is_not_reachable_from_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "libss_emu" not in src and "simt_emu.binding" not in src and "import simt_emu" not in src, f
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_results_do_not_depend_on_the_lane_schedule(kind):
+    """Threads of the kernels may only exchange data across warp collectives / block barriers.  The emulation resumes a
+    block's fibers in ascending, descending or a shuffled order per scheduling round: reset + control steps in contact
+    must be BIT-identical under all three (a kernel leaning on lock-step execution between two collectives would not be)."""
+    from simt_emu import binding
+    lib = binding.load()
+    n = 5
+    out = []
+    warm = make_oracle(kind, n)
+    warm.reset()
+    rng = np.random.RandomState(3)
+    for _ in range(14):
+        warm.step(random_actions(rng, n))                       # falling / first contacts
+    st0 = warm.get_state(); warm.close()
+    acts = [random_actions(rng, n) for _ in range(3)]
+    try:
+        for order in (0, 1, 2):
+            lib.simt_emu_set_order(order)
+            g = EmuEnv(kind, n)
+            obs0 = g.reset()
+            g.set_state(st0)
+            res = [g.step(a) for a in acts]
+            out.append((obs0, [r[0] for r in res], [r[1] for r in res], g.get_state()))
+            g.close()
+    finally:
+        lib.simt_emu_set_order(0)
+    for other in out[1:]:
+        assert np.array_equal(out[0][0], other[0])
+        for a, b in zip(out[0][1], other[1]):
+            assert np.array_equal(a, b)
+        for a, b in zip(out[0][2], other[2]):
+            assert np.array_equal(a, b)
+        for k in ("q", "qd", "warm", "terrain", "scalars", "ints", "mt"):
+            assert np.array_equal(out[0][3][k], other[3][k]), k
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_emulated_aba_substep_kernel(kind):
+    """aba_substep_kernel (the metric's "ABA kernel"): tolerances of tests/test_gpu_parity.py::test_aba_substep_parity."""
+    n = 24
+    o = make_oracle(kind, 1); g = EmuEnv(kind, 2)
+    rng = np.random.RandomState(2)
+    q = np.zeros((n, 28)); qd = rng.randn(n, 27)
+    q[:, :3] = rng.randn(n, 3)
+    quat = rng.randn(n, 4); q[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    q[:, 7:] = rng.uniform(-0.5, 0.5, (n, 21))
+    tau = rng.randn(n, 21) * 20
+    qo, qdo = o.aba_substep(q, qd, tau)
+    qg, qdg = g.aba_substep(q, qd, tau)
+    assert np.max(np.abs(qdo - qdg) / np.maximum(1.0, np.abs(qdo))) < 5e-4
+    assert _maxerr(qo, qg) < 1e-5
+    o.close(); g.close()
+
+
+def test_emulated_gae_kernel():
+    T, N = 19, 70
+    rng = np.random.RandomState(0)
+    o = make_oracle(0, 1); g = EmuEnv(0, 1)
+    r = rng.randn(T, N).astype(np.float32); v = rng.randn(T + 1, N).astype(np.float32)
+    m = (rng.rand(T + 1, N) > 0.1).astype(np.float32); bm = (rng.rand(T + 1, N) > 0.05).astype(np.float32)
+    assert np.max(np.abs(g.gae(r, v, m, bm, 0.99, 0.95)[:T] - o.gae(r, v, m, bm, 0.99, 0.95)[:T])) < 1e-4
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("kind,variant", [(0, 1), (1, 2)])
+def test_emulated_temp_state_kernels(kind, variant):
+    """temp_prep_kernel + temp_fill_kernel (create_temp_states_1 / _2) incl. the zero rows and the side effects."""
+    from steppingstone_b200 import seeding
+    n = 6
+    o = make_oracle(kind, n); g = EmuEnv(kind, n)
+    if kind == 1:
+        cdf = seeding.choice_cdf(seeding.curriculum_table(5)); o.set_sample_cdf(cdf); g.set_sample_cdf(cdf)
+    o.reset(); g.reset()
+    st = o.get_state()
+    # as tests/test_gpu_parity.py::_force_advance: a foot contact on the target with the dwell counter one short
+    st["ints"][:, 1] = 29; st["scalars"][:, 14:16] = 1.0
+    tgt = st["terrain"][np.arange(n), st["ints"][:, 0]]
+    st["q"][:, 0:2] = tgt[:, 0:2]; st["q"][:, 2] = tgt[:, 2] + 0.9
+    st["ints"][::3, 1] = 3                                         # every third env does NOT advance -> zero rows
+    o.set_state(st); g.set_state(st)
+    a = np.zeros((n, 21), np.float32)
+    o.env_post(a); g.env_post(a)
+    ts_o = o.create_temp_states(variant, seeding.fake_sample_grid(), seeding.temp_state_restore(kind))
+    ts_g = g.create_temp_states(variant, seeding.fake_sample_grid(), seeding.temp_state_restore(kind))
+    assert ts_o.shape == ts_g.shape
+    assert not ts_g[::3].any() and np.abs(ts_o[1]).max() > 0
+    cols = np.ones(60, bool)
+    if kind == 1:
+        cols[6:9] = False
+    assert np.max(np.abs(ts_o - ts_g)[:, :, cols]) < 2e-4
+    assert _maxerr(o.get_state()["terrain"], g.get_state()["terrain"]) < 1e-9
+    o.close(); g.close()

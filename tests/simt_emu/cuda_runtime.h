@@ -76,7 +76,8 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFunc
 namespace simt {
 
 struct Fiber {
-    ucontext_t ctx;
+    ucontext_t ctx;           // portable fallback
+    void* sp = nullptr;       // x86-64: saved stack pointer of the hand-written switch (no sigprocmask syscall per switch)
     char* stack = nullptr;
     dim3 tid;
     int lane = 0, warp = 0;
@@ -92,6 +93,7 @@ struct Block {
     std::vector<Fiber> fibers;
     std::vector<WarpCtx> warps;
     ucontext_t sched;
+    void* sched_sp = nullptr;
     Fiber* cur = nullptr;
     int nthreads = 0, live = 0, bar_arrived = 0;
     unsigned bar_gen = 0;
@@ -101,7 +103,7 @@ struct Block {
 extern Block* g_block;
 extern unsigned char* g_dynsmem;
 
-static inline void yield() { Fiber* f = g_block->cur; swapcontext(&f->ctx, &g_block->sched); }
+void yield();             // back to the block's scheduler (emu_runtime.cpp)
 
 // rendez-vous of the live lanes of the calling fiber's warp: deposit `bits`, wait for the others, then `read` sees every
 // lane's deposit in slot[]; buffers alternate by collective parity, so a lane that is already depositing for the next

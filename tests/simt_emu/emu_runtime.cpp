@@ -11,6 +11,44 @@ unsigned char* g_dynsmem = nullptr;
 static int g_order = 0;
 static const size_t STACK = 512 * 1024;
 
+#if defined(__x86_64__)
+#define SIMT_ASM_SWITCH 1
+// save the callee-saved registers on the current stack, store its pointer in *from, continue on the stack *to
+extern "C" void simt_swap(void** from, void** to);
+asm(R"(
+.text
+.globl simt_swap
+.type simt_swap,@function
+simt_swap:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq (%rsi), %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size simt_swap,.-simt_swap
+)");
+#endif
+
+void yield() {
+    Block* b = g_block;
+    Fiber* f = b->cur;
+#ifdef SIMT_ASM_SWITCH
+    simt_swap(&f->sp, &b->sched_sp);
+#else
+    swapcontext(&f->ctx, &b->sched);
+#endif
+}
+
 static void fiber_exit_bookkeeping(Block* b, Fiber* f) {
     f->done = true;
     b->live--;
@@ -24,14 +62,21 @@ static void trampoline() {
     Fiber* f = b->cur;
     b->body();
     fiber_exit_bookkeeping(b, f);
-    swapcontext(&f->ctx, &b->sched);      // never resumed
+    yield();                              // never resumed
+    abort();
 }
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     const int nthreads = (int)(block.x * block.y * block.z);
     const int nwarps = (nthreads + 31) / 32;
-    std::vector<char> stacks((size_t)nthreads * STACK);
-    std::vector<unsigned char> dyn(smem + 64);
+    // fiber stacks and the dynamic shared-memory window are kept between launches (a fresh std::vector would zero-fill
+    // 512 KB per thread on every launch)
+    static char* stack_pool = nullptr; static size_t stack_pool_size = 0;
+    static unsigned char* dyn_pool = nullptr; static size_t dyn_pool_size = 0;
+    if ((size_t)nthreads * STACK > stack_pool_size) { free(stack_pool); stack_pool_size = (size_t)nthreads * STACK; stack_pool = (char*)malloc(stack_pool_size); }
+    if (smem + 64 > dyn_pool_size) { free(dyn_pool); dyn_pool_size = smem + 64; dyn_pool = (unsigned char*)malloc(dyn_pool_size); }
+    struct { char* p; char* data() { return p; } } stacks{ stack_pool };
+    struct { unsigned char* p; unsigned char* data() { return p; } } dyn{ dyn_pool };
     for (unsigned bz = 0; bz < grid.z; bz++)
         for (unsigned by = 0; by < grid.y; by++)
             for (unsigned bx = 0; bx < grid.x; bx++) {
@@ -48,11 +93,23 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                     Fiber& f = b.fibers[t];
                     f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
                     f.lane = t & 31; f.warp = t >> 5;
+#ifdef SIMT_ASM_SWITCH
+                    {   // initial frame: six zeroed callee-saved registers, then the entry point as the return address;
+                        // after the `ret` the stack pointer is 8 below a 16-byte boundary, as at any function entry
+                        uintptr_t top = ((uintptr_t)(stacks.data() + (size_t)(t + 1) * STACK)) & ~(uintptr_t)15;
+                        void** sp = (void**)(top - 8);
+                        *sp = nullptr;
+                        *--sp = (void*)trampoline;
+                        for (int r = 0; r < 6; r++) *--sp = nullptr;
+                        f.sp = sp;
+                    }
+#else
                     getcontext(&f.ctx);
                     f.ctx.uc_stack.ss_sp = stacks.data() + (size_t)t * STACK;
                     f.ctx.uc_stack.ss_size = STACK;
                     f.ctx.uc_link = &b.sched;
                     makecontext(&f.ctx, trampoline, 0);
+#endif
                 }
                 long rounds = 0;
                 uint32_t lcg = 12345u;
@@ -65,7 +122,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
                         Fiber& f = b.fibers[t];
                         if (f.done) continue;
                         b.cur = &f;
+#ifdef SIMT_ASM_SWITCH
+                        simt_swap(&b.sched_sp, &f.sp);
+#else
                         swapcontext(&b.sched, &f.ctx);
+#endif
                     }
                     if (++rounds > 50000000L) { fprintf(stderr, "simt_emu: block (%u,%u) does not terminate (divergent collective?)\n", bx, by); abort(); }
                 }

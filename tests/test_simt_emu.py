@@ -204,3 +204,75 @@ def test_emulated_temp_state_kernels(kind, variant):
     assert np.max(np.abs(ts_o - ts_g)[:, :, cols]) < 2e-4
     assert _maxerr(o.get_state()["terrain"], g.get_state()["terrain"]) < 1e-9
     o.close(); g.close()
+
+
+def test_emulated_resample_kernel():
+    """resample_kernel (update_sample_prob's immediate re-draw for the envs that just advanced a stone) + the later draws
+    from the new table: CPU twin of tests/test_gpu_parity.py::test_update_sample_prob_resamples_flagged_envs -- the test
+    that found the stale-scratch bug of this kernel on the device."""
+    from steppingstone_b200 import seeding
+    n = 10
+    o = make_oracle(1, n); g = EmuEnv(1, n)
+    cdf5 = seeding.choice_cdf(seeding.curriculum_table(5))
+    o.set_sample_cdf(cdf5); g.set_sample_cdf(cdf5)
+    o.reset(); g.reset()
+
+    def force_advance(st):
+        st["ints"][:, 1] = 29; st["scalars"][:, 14:16] = 1.0
+        tgt = st["terrain"][np.arange(n), st["ints"][:, 0]]
+        st["q"][:, 0:2] = tgt[:, 0:2]; st["q"][:, 2] = tgt[:, 2] + 0.9
+
+    st = o.get_state(); force_advance(st)
+    st["ints"][::2, 1] = 3                       # every other env does not advance: no immediate re-sample there
+    o.set_state(st); g.set_state(st)
+    a = np.zeros((n, 21), np.float32)
+    o.env_post(a); g.env_post(a)
+    rng = np.random.RandomState(12)
+    table = (rng.rand(11, 11, 11, 11, 11) * (rng.rand(11, 11, 11, 11, 11) < 0.02)).astype(np.float32).astype(np.float64)
+    table[5, 5, 0, 5, 5] += 1e-3
+    before = o.get_state()["terrain"].copy()
+    cdf = seeding.choice_cdf(table)
+    o.set_sample_cdf(cdf, apply_now=True); g.set_sample_cdf(cdf, apply_now=True)
+    so, sg = o.get_state(), g.get_state()
+    changed = np.abs(so["terrain"] - before).max(axis=(1, 2)) > 0
+    assert changed[1::2].all() and not changed[::2].any()
+    assert np.array_equal(so["mt"], sg["mt"]) and np.array_equal(so["ints"], sg["ints"])
+    assert _maxerr(so["terrain"], sg["terrain"]) < 1e-9 and _maxerr(so["plank"], sg["plank"]) < 1e-9
+    st = o.get_state(); force_advance(st); o.set_state(st); g.set_state(st)
+    o.env_post(a); g.env_post(a)
+    so, sg = o.get_state(), g.get_state()
+    assert np.array_equal(so["mt"], sg["mt"]) and _maxerr(so["terrain"], sg["terrain"]) < 1e-9
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_emulated_whole_steps_with_auto_reset(kind):
+    """Whole control steps (4 chained substeps, observation, reward, termination, Monitor bookkeeping) and the auto-reset
+    inside the step kernel (terrain generator on the env's MT19937 stream), each step teacher-forced from the oracle's
+    state so that the chaotic contact dynamics cannot drift: episode ends agree, the post-reset observation and the RNG
+    streams of the envs that ended are identical."""
+    n = 5
+    o = make_oracle(kind, n); g = EmuEnv(kind, n)
+    o.reset(); g.reset()
+    rng = np.random.RandomState(5)
+    n_done = n_mismatch = 0
+    for t in range(30):
+        a = random_actions(rng, n, sd=1.0)                      # saturated torques: the robots fall within ~25 steps
+        g.set_state(o.get_state())
+        obs_o, rew_o, done_o, to_o, er_o, el_o = o.step(a)
+        obs_g, rew_g, done_g, to_g, er_g, el_g = g.step(a)
+        done_o = done_o.astype(bool)
+        n_mismatch += int((done_o != done_g).sum())
+        both = done_o & done_g
+        if both.any():
+            n_done += int(both.sum())
+            so, sg = o.get_state(), g.get_state()
+            assert np.array_equal(so["mt"][both], sg["mt"][both]), "RNG streams differ after the auto-reset"
+            assert _maxerr(so["terrain"][both], sg["terrain"][both]) < 1e-9
+            assert _maxerr(obs_o[both], obs_g[both]) < 1e-5, "post-reset observation"
+            assert np.array_equal(el_o[both], el_g[both])
+            assert _maxerr(er_o[both], er_g[both]) < 1e-2 * max(1.0, float(np.abs(er_o[both]).max()))
+        calm = ~done_o & ~done_g
+        assert np.abs(rew_o - rew_g)[calm].max(initial=0.0) < 0.5      # 4 chained substeps in fp32, saturated torques
+    assert n_done >= 3 and n_mismatch <= 1, (n_done, n_mismatch)
+    o.close(); g.close()

@@ -276,3 +276,22 @@ def test_emulated_whole_steps_with_auto_reset(kind):
         assert np.abs(rew_o - rew_g)[calm].max(initial=0.0) < 0.5      # 4 chained substeps in fp32, saturated torques
     assert n_done >= 3 and n_mismatch <= 1, (n_done, n_mismatch)
     o.close(); g.close()
+
+
+def test_shipped_policy_walks_on_the_emulated_kernels():
+    """The reference's flat-stage policy (playground/models/..._base.pt) driving the PRODUCT's kernels closed-loop for 450
+    control steps: ~14 stones per env (a stone needs 30 dwell frames) -- tests/test_policy_behaviour.py on the device code
+    itself, without a device."""
+    from test_policy_behaviour import actor_numpy, load_actor
+    n = 3
+    P = load_actor("w3d_base.npz")
+    g = EmuEnv(0, n, terrain_mode=2)
+    obs = g.reset()
+    total = np.zeros(n)
+    for t in range(450):
+        obs, rew, done, _, _, _ = g.step(actor_numpy(P, obs))
+        assert not done.any(), "fell at step %d" % t
+        total += rew
+    stones = g.get_state()["ints"][:, 0]
+    g.close()
+    assert (stones >= 12).all() and (total > 1500).all(), (stones, total)

@@ -225,6 +225,7 @@ __device__ __forceinline__ Xf fk_warp(const DevModel& M, const float* quat, floa
 }
 
 // LDL^T elimination step K (lane i owns row i of the symmetric matrix); compile-time recursion keeps Hr in registers
+#if !defined(SS_SPARSE_LDL) || !SS_SPARSE_LDL
 template <int K>
 __device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int lane) {
     if constexpr (K < ND) {
@@ -241,6 +242,53 @@ __device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int la
         ldl_steps<K + 1>(Hr, myDinv, lane);
     }
 }
+#endif
+
+#ifndef SS_SPARSE_LDL
+#define SS_SPARSE_LDL 0
+#endif
+#if SS_SPARSE_LDL
+// EXPERIMENT (default off; verified on the SIMT emulation, not yet timed on a B200): branch-induced sparsity.
+// H[i][k] != 0 only if dof i is an ancestor of dof k or vice versa.  Eliminating the dofs leaves-first (k descending)
+// creates no fill-in: H = U D U^T with U unit upper triangular and U[i][k] != 0 only for i a proper ancestor of k
+// (Featherstone's L^T D L).  206 instead of 351 + 27 non-zeros for this humanoid: the factorisation needs one shuffle
+// per (k, ancestor of k) pair and the triangular solves skip the structural zeros at compile time.
+__host__ __device__ constexpr bool body_anc(int a, int b) {          // body a is a proper ancestor of body b
+    constexpr int parent[NB] = SS_PARENT_TABLE;
+    for (int x = parent[b]; x >= 0; x = parent[x]) if (x == a) return true;
+    return false;
+}
+// dof numbering: 0..5 the floating base (a chain in front of everything), 6 + j the hinge of body j + 1
+__host__ __device__ constexpr bool dof_anc(int i, int k) { return i < k && k < ND && (i < 6 || body_anc(i - 5, k - 5)); }
+__host__ __device__ constexpr unsigned anc_lanes(int k) { unsigned m = 0; for (int i = 0; i < k; i++) if (dof_anc(i, k)) m |= 1u << i; return m; }
+
+template <int K, int J>
+__device__ __forceinline__ void udu_cols(float (&Hr)[HS], float uik, bool mine) {
+    if constexpr (J >= 0) {
+        if constexpr (dof_anc(J, K)) {
+            float hkj = shfl(Hr[J], K);
+            if (mine) Hr[J] -= uik * hkj;
+        }
+        udu_cols<K, J - 1>(Hr, uik, mine);
+    }
+}
+// U D U^T elimination step K, K descending (lane i owns the full symmetric row i): after the last step lane i holds
+// U[i][k] in Hr[k] for k > i; columns k <= i are scratch
+template <int K>
+__device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int lane) {
+    if constexpr (K >= 0) {
+        float dk = shfl(Hr[K], K);
+        float inv = 1.f / dk;
+        if (lane == K) myDinv = inv;
+        constexpr unsigned lanes = anc_lanes(K);
+        const bool mine = (lanes >> lane) & 1u;
+        float uik = Hr[K] * inv;
+        udu_cols<K, K - 1>(Hr, uik, mine);
+        if (mine) Hr[K] = uik;
+        ldl_steps<K - 1>(Hr, myDinv, lane);
+    }
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // dynamics: builds H (joint-space inertia, common frame) and its LDL^T in shared memory, returns the
@@ -418,7 +466,11 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
         }
     }
     float myDinv = 1.f;
+#if SS_SPARSE_LDL
+    ldl_steps<ND - 1>(Hr, myDinv, lane);
+#else
     ldl_steps<0>(Hr, myDinv, lane);
+#endif
     if (lane < ND) {
         float4* row = reinterpret_cast<float4*>(H + lane * HS);
 #pragma unroll
@@ -428,19 +480,61 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
     __syncwarp();
     // solve H acc = rhs
     float y = rhs;
+#if SS_SPARSE_LDL
+    // U y' = rhs (k descending; Hr[k] = U[lane][k], structurally zero where lane is no ancestor of k), D, U^T x = y''
+#pragma unroll
+    for (int k = ND - 1; k >= 1; k--) { float yk = shfl(y, k); if (lane < k) y -= Hr[k] * yk; }
+    y *= myDinv;
+#pragma unroll 1
+    for (int k = 0; k < ND - 1; k++) { float xk = shfl(y, k); if (lane > k && lane < ND) y -= H[k * HS + lane] * xk; }
+#else
 #pragma unroll
     for (int k = 0; k < ND - 1; k++) { float yk = shfl(y, k); if (lane > k && lane < ND) y -= Hr[k] * yk; }
     y *= myDinv;
 #pragma unroll 1
     for (int k = ND - 1; k >= 1; k--) { float xk = shfl(y, k); if (lane < k) y -= H[k * HS + lane] * xk; }
+#endif
     return lane < ND ? y : 0.f;
 }
+
+#if SS_SPARSE_LDL
+// one row of the back-substitution z = U^-1 b (lane = constraint row; U rows are broadcast LDS.128 reads): quads of row I
+// that hold no descendant of dof I are not even loaded
+template <int I, int Q>
+__device__ __forceinline__ void sparse_urow(const float4* Ui, const float (&z)[HS], float& acc) {
+    if constexpr (4 * Q < ND) {
+        constexpr bool a0 = dof_anc(I, 4 * Q), a1 = dof_anc(I, 4 * Q + 1), a2 = dof_anc(I, 4 * Q + 2), a3 = dof_anc(I, 4 * Q + 3);
+        if constexpr (a0 || a1 || a2 || a3) {
+            const float4 u = Ui[Q];
+            if constexpr (a0) acc = fmaf(-u.x, z[4 * Q], acc);
+            if constexpr (a1) acc = fmaf(-u.y, z[4 * Q + 1], acc);
+            if constexpr (a2) acc = fmaf(-u.z, z[4 * Q + 2], acc);
+            if constexpr (a3) acc = fmaf(-u.w, z[4 * Q + 3], acc);
+        }
+        sparse_urow<I, Q + 1>(Ui, z, acc);
+    }
+}
+template <int I>
+__device__ __forceinline__ void sparse_usolve(const float* U, float (&z)[HS]) {
+    if constexpr (I >= 0) {
+        float acc = z[I];
+        sparse_urow<I, (I + 1) / 4>(reinterpret_cast<const float4*>(U + I * HS), z, acc);
+        z[I] = acc;
+        sparse_usolve<I - 1>(U, z);
+    }
+}
+#endif
 
 // back-substitution L^T x = u (lane = dof)
 __device__ __forceinline__ float solve_lt(const WarpSmem& W, float u, int lane) {
     const float* H = W.u.s.H;
+#if SS_SPARSE_LDL
+#pragma unroll 1
+    for (int k = 0; k < ND - 1; k++) { float xk = shfl(u, k); if (lane > k && lane < ND) u -= H[k * HS + lane] * xk; }   // U^T x = u
+#else
 #pragma unroll 1
     for (int k = ND - 1; k >= 1; k--) { float xk = shfl(u, k); if (lane < k) u -= H[k * HS + lane] * xk; }
+#endif
     return u;
 }
 
@@ -872,6 +966,9 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
             rel += pass == 0 ? relp : -relp;
             // forward substitution with the unit lower factor, row by row (broadcast LDS.128 reads of L)
             const float* L = W.u.s.H;
+#if SS_SPARSE_LDL
+            sparse_usolve<ND - 2>(L, z);         // z = U^-1 J^T, rows from the leaves to the root, structural zeros skipped
+#else
 #pragma unroll
             for (int i = 1; i < ND; i++) {
                 const float4* Li = reinterpret_cast<const float4*>(L + i * HS);
@@ -886,6 +983,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 }
                 z[i] = acc;
             }
+#endif
             if (npass == 2) {
 #pragma unroll
                 for (int k = 0; k < ND; k++) dsides = fmaf(z[k] * W.dinv[k], z[k], dsides);

@@ -14,23 +14,24 @@ from steppingstone_b200 import model, native, seeding
 from . import build_emu
 
 OBS, NJ = 60, 21
-_lib = None
+_libs = {}
+VARIANTS = {"": (), "sparse": ("-DSS_SPARSE_LDL=1",)}      # tag -> extra compile flags (kernel variants kept verified)
 
 
-def load():
-    global _lib
-    if _lib is None:
-        lib = ctypes.CDLL(build_emu.build())
+def load(variant=""):
+    if variant not in _libs:
+        lib = ctypes.CDLL(build_emu.build(extra_flags=VARIANTS[variant], tag=variant))
         for name, (res, args) in native._SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        _lib = lib
-    return _lib
+        lib.simt_emu_collectives.restype = ctypes.c_ulonglong
+        _libs[variant] = lib
+    return _libs[variant]
 
 
 class EmuEnv:
-    def __init__(self, kind, n, seed=8, params=None, terrain_mode=None):
-        self.lib = load()
+    def __init__(self, kind, n, seed=8, params=None, terrain_mode=None, variant=""):
+        self.lib = load(variant)
         self.n = n
         self.model = model.make_model(kind)
         self.params = model.make_params(kind, params, terrain_mode)

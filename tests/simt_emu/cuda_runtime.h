@@ -102,6 +102,7 @@ struct Block {
 };
 extern Block* g_block;
 extern unsigned char* g_dynsmem;
+extern unsigned long long g_collectives;   // warp collectives executed (per lane), a cheap work counter for kernel variants
 
 void yield();             // back to the block's scheduler (emu_runtime.cpp)
 
@@ -114,6 +115,7 @@ static inline auto warp_collective(uint64_t bits, R read) {
     WarpCtx& w = g_block->warps[f->warp];
     const int p = f->op & 1;
     f->op++;
+    g_collectives++;
     w.slot[p][f->lane] = bits;
     w.arrived[p]++;
     while (w.arrived[p] < w.live) yield();

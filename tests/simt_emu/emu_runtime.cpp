@@ -5,6 +5,7 @@ namespace simt {
 
 Block* g_block = nullptr;
 unsigned char* g_dynsmem = nullptr;
+unsigned long long g_collectives = 0;
 // 0: lanes are resumed in ascending order within every scheduling round, 1: descending, 2: a fixed pseudo-random
 // permutation per round.  A kernel whose threads only communicate across collectives / barriers gives bit-identical
 // results under every order; one that relies on lock-step execution does not (a poor man's racecheck).
@@ -137,3 +138,4 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 }  // namespace simt
 
 extern "C" void simt_emu_set_order(int order) { simt::g_order = order; }
+extern "C" unsigned long long simt_emu_collectives() { return simt::g_collectives; }

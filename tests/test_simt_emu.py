@@ -295,3 +295,39 @@ def test_shipped_policy_walks_on_the_emulated_kernels():
     stones = g.get_state()["ints"][:, 0]
     g.close()
     assert (stones >= 12).all() and (total > 1500).all(), (stones, total)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_sparse_factorisation_variant_stays_correct(kind):
+    """-DSS_SPARSE_LDL=1 (default off until it has been timed on a B200): branch-induced sparsity of the joint-space inertia,
+    H = U D U^T eliminated leaves-first, structural zeros skipped at compile time in the factorisation and the triangular
+    solves.  Same per-substep comparison against the oracle as the default build, in contact; fewer warp collectives."""
+    n = 6
+    prm = dict(n_substeps=1)
+    o = make_oracle(kind, n, params=prm)
+    g = EmuEnv(kind, n, params=prm, variant="sparse"); d = EmuEnv(kind, n, params=prm)
+    o.reset(); g.reset(); d.reset()
+    rng0 = np.random.RandomState(7)
+    for _ in range(40):
+        o.step(random_actions(rng0, n))
+    g.enable_substep_trace(True)
+    rng = np.random.RandomState(107)
+    worst_v = worst_q = 0.0
+    count = {}
+    for s in range(6):
+        a = random_actions(rng, n)
+        st = o.get_state(); g.set_state(st); d.set_state(st)
+        o.step(a)
+        for name, env in (("sparse", g), ("dense", d)):
+            c0 = env.lib.simt_emu_collectives(); env.step(a); count[name] = count.get(name, 0) + env.lib.simt_emu_collectives() - c0
+        qo, qdo = o.substep_trace(); qg, qdg = g.substep_trace()
+        vscale = np.maximum(1.0, np.abs(qdo[0]).max(axis=1, keepdims=True))
+        worst_v = max(worst_v, float(np.max(np.abs(qdo[0] - qdg[0]) / vscale))); worst_q = max(worst_q, _maxerr(qo[0], qg[0]))
+    qa = np.random.RandomState(2).uniform(-0.5, 0.5, (8, 28)); qa[:, 3:7] /= np.linalg.norm(qa[:, 3:7], axis=1, keepdims=True)
+    qd = np.random.RandomState(3).randn(8, 27); tau = np.random.RandomState(4).randn(8, 21) * 20
+    ref = make_oracle(kind, 1)
+    qo2, qdo2 = ref.aba_substep(qa, qd, tau); qg2, qdg2 = g.aba_substep(qa, qd, tau)
+    o.close(); g.close(); d.close(); ref.close()
+    assert worst_v < 1e-3 and worst_q < 5e-6, (worst_v, worst_q)
+    assert np.max(np.abs(qdo2 - qdg2) / np.maximum(1.0, np.abs(qdo2))) < 5e-4 and _maxerr(qo2, qg2) < 1e-5
+    assert count["sparse"] < 0.92 * count["dense"], count          # ~145 of ~1300 collectives per env-substep gone

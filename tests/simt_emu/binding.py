@@ -15,7 +15,9 @@ from . import build_emu
 
 OBS, NJ = 60, 21
 _libs = {}
-VARIANTS = {"": (), "sparse": ("-DSS_SPARSE_LDL=1",)}      # tag -> extra compile flags (kernel variants kept verified)
+# tag -> extra compile flags: kernel variants kept verified, and the production CTA shape (20 warps per CTA: ghost warps,
+# per-substep block barrier, contact-sorted env order) next to the default one-warp-per-CTA emulation build
+VARIANTS = {"": (), "sparse": ("-DSS_SPARSE_LDL=1",), "wpb20": ("-DSS_WPB=20",)}
 
 
 def load(variant=""):

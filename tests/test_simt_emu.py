@@ -331,3 +331,37 @@ def test_sparse_factorisation_variant_stays_correct(kind):
     assert worst_v < 1e-3 and worst_q < 5e-6, (worst_v, worst_q)
     assert np.max(np.abs(qdo2 - qdg2) / np.maximum(1.0, np.abs(qdo2))) < 5e-4 and _maxerr(qo2, qg2) < 1e-5
     assert count["sparse"] < 0.92 * count["dense"], count          # ~145 of ~1300 collectives per env-substep gone
+
+
+def test_production_cta_shape_on_the_emulation():
+    """The shipped launch configuration -- 20 warps per CTA, ghost warps in the last CTA that only keep the per-substep
+    block barrier company, envs handed to warps in contact-count order (sort kernels + perm) -- with 85 envs = 4 full CTAs
+    + 5 envs and 15 ghost warps: identical results to the one-warp-per-CTA emulation build (which warp steps which env
+    never changes a result), under two fiber schedules."""
+    n = 85
+    o = make_oracle(0, n)
+    o.reset()
+    rng = np.random.RandomState(9)
+    for _ in range(12):
+        o.step(random_actions(rng, n))
+    st = o.get_state(); o.close()
+    acts = [random_actions(rng, n) for _ in range(2)]
+    res = {}
+    for variant, order in (("", 0), ("wpb20", 0), ("wpb20", 1)):
+        g = EmuEnv(0, n, variant=variant)
+        g.lib.simt_emu_set_order(order)
+        try:
+            g.reset(); g.set_state(st)
+            out = [g.step(a) for a in acts]
+            res[(variant, order)] = (out, g.get_state())
+        finally:
+            g.lib.simt_emu_set_order(0)
+            g.close()
+    ref_out, ref_st = res[("", 0)]
+    for key in (("wpb20", 0), ("wpb20", 1)):
+        out, stt = res[key]
+        for a, b in zip(ref_out, out):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), key
+        for k in ("q", "qd", "warm", "scalars", "ints", "mt", "terrain"):
+            assert np.array_equal(ref_st[k], stt[k]), (key, k)

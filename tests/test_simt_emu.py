@@ -365,3 +365,23 @@ def test_production_cta_shape_on_the_emulation():
                 assert np.array_equal(x, y), key
         for k in ("q", "qd", "warm", "scalars", "ints", "mt", "terrain"):
             assert np.array_equal(ref_st[k], stt[k]), (key, k)
+
+
+def test_plain_c_host_runs_against_the_emulated_library(tmp_path):
+    """examples/c_host.c (the host-without-Python example of INTEGRATION.md) linked against the emulated library instead of
+    libss_b200.so: the C-ABI of include/ss_env.h end to end from plain C -- ss_create, ss_reset_host, ss_step_host with
+    host buffers, ss_destroy -- the CPU twin of tests/test_abi.py::test_c_host_runs_on_gpu."""
+    import subprocess
+    import sys
+    from simt_emu import build_emu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = build_emu.build()
+    exe = str(tmp_path / "c_host_emu")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "examples", "c_host.c"), lib, "-Wl,-rpath," + os.path.dirname(lib), "-lm"])
+    tables = str(tmp_path / "tables")
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "dump_tables.py"), tables, "walker3d", "8", "8"],
+                          stdout=subprocess.DEVNULL)
+    res = subprocess.run([exe, tables, "8", "30"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert "env-steps/s" in res.stdout and "episodes finished" in res.stdout

@@ -103,6 +103,9 @@ def load():
     override = os.environ.get("SS_B200_LIB")          # experiments only: a differently-tuned build of the same sources
     if override:
         lib = ctypes.CDLL(override)
+        if hasattr(lib, "simt_emu_set_order"):
+            # the host-side SIMT emulation of tests/ is test infrastructure: the product has no CPU path
+            raise RuntimeError("SS_B200_LIB points at the SIMT emulation build; the product path needs the CUDA library")
     else:
         if needs_build():
             build_native()

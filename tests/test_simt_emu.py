@@ -101,6 +101,18 @@ def test_emulated_kernels_on_walking_states(case):
     assert worst_v < 1e-3 and worst_q < 5e-6, (worst_v, worst_q)
 
 
+def test_product_loader_refuses_the_emulated_library():
+    """Even the experiment hook of the product's loader (SS_B200_LIB, a differently-tuned CUDA build) will not take it."""
+    import subprocess
+    import sys
+    from simt_emu import build_emu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SS_B200_LIB=build_emu.build())
+    code = "import sys; sys.path.insert(0, %r); from steppingstone_b200 import native; native.load()" % root
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode != 0 and "SIMT emulation" in res.stderr
+
+
 def test_emulation_is_not_reachable_from_the_product():
     """The emulated library lives under tests/ and has its own binding: the package never names it."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -108,6 +108,22 @@ struct alignas(16) WarpSmemDyn {
 // small helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// Reciprocal / division / square root of the hot path.  The IEEE-rounded forms compile to a MUFU + Newton steps + a
+// slow-path check each (~8-10 instructions, 40 of them per env-substep, 27 on the critical path of the factorisation);
+// the approximate forms (<= 1-2 ulp) are one MUFU.  The difference is below the fp32 rounding noise the parity
+// tolerances already carry (GPU fp32 vs oracle fp64).  -DSS_FAST_DIV=0 restores the IEEE forms.
+#ifndef SS_FAST_DIV
+#define SS_FAST_DIV 1
+#endif
+#if SS_FAST_DIV && !defined(SS_SIMT_EMU)
+__device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }
+__device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+__device__ __forceinline__ float frcp(float x) { return 1.f / x; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
+#endif
 __device__ __forceinline__ float shfl(float v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -230,7 +246,7 @@ template <int K>
 __device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int lane) {
     if constexpr (K < ND) {
         float dk = shfl(Hr[K], K);
-        float inv = 1.f / dk;
+        float inv = frcp(dk);
         if (lane == K) myDinv = inv;
         float lik = Hr[K] * inv;
 #pragma unroll
@@ -278,7 +294,7 @@ template <int K>
 __device__ __forceinline__ void ldl_steps(float (&Hr)[HS], float& myDinv, int lane) {
     if constexpr (K >= 0) {
         float dk = shfl(Hr[K], K);
-        float inv = 1.f / dk;
+        float inv = frcp(dk);
         if (lane == K) myDinv = inv;
         constexpr unsigned lanes = anc_lanes(K);
         const bool mine = (lanes >> lane) & 1u;
@@ -560,9 +576,9 @@ __device__ __forceinline__ void integrate_warp(const DevModel& M, float* quat, f
     for (int i = 0; i < 3; i++) { w[i] = shfl(vnew, i); vl[i] = shfl(vnew, 3 + i); }
 #pragma unroll
     for (int i = 0; i < 3; i++) dpos[i] += vl[i] * hdt;
-    float ang = sqrtf(dot3(w, w));
-    if (ang * hdt > 0.78539816f) ang = 0.78539816f / hdt;
-    float f = ang < 0.001f ? 0.5f * hdt - hdt * hdt * hdt * 0.020833333333f * ang * ang : sinf(0.5f * ang * hdt) / ang;
+    float ang = fsqrt(dot3(w, w));
+    if (ang * hdt > 0.78539816f) ang = fdiv(0.78539816f, hdt);
+    float f = ang < 0.001f ? 0.5f * hdt - hdt * hdt * hdt * 0.020833333333f * ang * ang : fdiv(sinf(0.5f * ang * hdt), ang);
     float dq[4] = { w[0] * f, w[1] * f, w[2] * f, cosf(0.5f * ang * hdt) }, rq[4];
     rq[0] = dq[3] * quat[0] + dq[0] * quat[3] + dq[1] * quat[2] - dq[2] * quat[1];
     rq[1] = dq[3] * quat[1] - dq[0] * quat[2] + dq[1] * quat[3] + dq[2] * quat[0];
@@ -661,7 +677,8 @@ __device__ __forceinline__ void stone_candidate(const DevModel& M, const float* 
         float d = b[ax] - a[ax], hh = M.stone_half[ax];
         if (fabsf(d) < 1e-12f) { if (fabsf(a[ax]) > hh) empty = true; }
         else {
-            float ta = (-hh - a[ax]) / d, tb = (hh - a[ax]) / d;
+            const float id = frcp(d);
+            float ta = (-hh - a[ax]) * id, tb = (hh - a[ax]) * id;
             if (ta > tb) { float s = ta; ta = tb; tb = s; }
             t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
         }
@@ -679,8 +696,8 @@ __device__ __forceinline__ void stone_candidate(const DevModel& M, const float* 
     }
     if (!inside) {
         float d[3] = { s[0] - q[0], s[1] - q[1], s[2] - q[2] };
-        dist = sqrtf(dot3(d, d));
-        float inv = 1.f / dist;
+        dist = fsqrt(dot3(d, d));
+        float inv = frcp(dist);
         nl[0] = d[0] * inv; nl[1] = d[1] * inv; nl[2] = d[2] * inv;
     } else {
         int ax = 0; float best = 1e30f;
@@ -713,16 +730,16 @@ __device__ __forceinline__ void segment_segment(const float* p1, const float* q1
     float s, t;
     auto clamp01 = [](float x) { return fminf(fmaxf(x, 0.f), 1.f); };
     if (a <= EPS && e <= EPS) { s = t = 0.f; }
-    else if (a <= EPS) { s = 0.f; t = clamp01(f / e); }
+    else if (a <= EPS) { s = 0.f; t = clamp01(fdiv(f, e)); }
     else {
         const float c = dot3(d1, r);
-        if (e <= EPS) { t = 0.f; s = clamp01(-c / a); }
+        if (e <= EPS) { t = 0.f; s = clamp01(fdiv(-c, a)); }
         else {
             const float b = dot3(d1, d2), denom = a * e - b * b;
-            s = denom > EPS * a * e ? clamp01((b * f - c * e) / denom) : 0.f;
-            t = (b * s + f) / e;
-            if (t < 0.f) { t = 0.f; s = clamp01(-c / a); }
-            else if (t > 1.f) { t = 1.f; s = clamp01((b - c) / a); }
+            s = denom > EPS * a * e ? clamp01(fdiv(b * f - c * e, denom)) : 0.f;
+            t = fdiv(b * s + f, e);
+            if (t < 0.f) { t = 0.f; s = clamp01(fdiv(-c, a)); }
+            else if (t > 1.f) { t = 1.f; s = clamp01(fdiv(b - c, a)); }
         }
     }
 #pragma unroll
@@ -795,11 +812,11 @@ __device__ __forceinline__ int collide_warp(const DevModel& M, WarpSmem& W, cons
                 segment_segment(A, A + 3, B, B + 3, ca, cb);
 #pragma unroll
                 for (int i = 0; i < 3; i++) d[i] = ca[i] - cb[i];
-                const float dist = sqrtf(dot3(d, d)), ra = A[6], rb = B[6];
+                const float dist = fsqrt(dot3(d, d)), ra = A[6], rb = B[6];
                 k.depth = dist - ra - rb;
                 if (k.depth < fminf(M.geom_breaking[ga], M.geom_breaking[gb])) {
                     k.active = true;
-                    if (dist > 1e-9f) { float inv = 1.f / dist; k.n[0] = d[0] * inv; k.n[1] = d[1] * inv; k.n[2] = d[2] * inv; }
+                    if (dist > 1e-9f) { float inv = frcp(dist); k.n[0] = d[0] * inv; k.n[1] = d[1] * inv; k.n[2] = d[2] * inv; }
                     else { k.n[0] = k.n[1] = 0.f; k.n[2] = 1.f; }
 #pragma unroll
                     for (int i = 0; i < 3; i++) { k.x[i] = ca[i] - ra * k.n[i]; k.xb[i] = cb[i] + rb * k.n[i]; }
@@ -1000,78 +1017,75 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 }
             }
         }
+        // the row's z goes to shared memory: the Delassus loop below reads it back chunk by chunk (so that z[] and the
+        // 32 Delassus entries never hold registers at the same time) and the final velocity update reads it with lane = dof
+        float diag = 0.f;
+#pragma unroll
+        for (int k = 0; k < ND; k++) diag = fmaf(z[k] * W.dinv[k], z[k], diag);
         {
             float4* Zr = reinterpret_cast<float4*>(Z + r * ZS);
 #pragma unroll
             for (int j = 0; j < ZS / 4; j++) Zr[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
         }
         __syncwarp();
-        // w = D^-1 z ; diagonal of the Delassus matrix first, so that the row can be stored pre-scaled
-        float diag = 0.f;
-#pragma unroll
-        for (int k = 0; k < ND; k++) { float w = z[k] * W.dinv[k]; diag = fmaf(w, z[k], diag); z[k] = w; }
         // row constants (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint / btMultiBodyJointLimitConstraint).
         // Stones are soft (contactStiffness / contactDamping -> cfm, erp); link-link contacts are hard (cfm 0, default contact ERP).
         float invD = 0.f, rhs = 0.f, cfmt = 0.f, lo = 0.f, hi = 0.f;
+        const float inv_h = frcp(hdt);
         if (selfrow && !M.self_cross_terms) diag = dsides;
         if (rtype == 0) {
-            invD = 1.f / diag;
-            rhs = (-pen * M.erp_limit / hdt - rel) * invD;
+            invD = frcp(diag);
+            rhs = (-pen * M.erp_limit * inv_h - rel) * invD;
             hi = M.limit_max_impulse;
         } else if (rtype >= 1) {
             const float cfm = selfrow ? 0.f : M.cfm_contact, erp = selfrow ? M.self_erp : M.erp_contact;
-            invD = 1.f / (diag + cfm);
+            invD = frcp(diag + cfm);
             cfmt = cfm * invD;
             if (rtype == 1) {
                 float p = pen + M.linear_slop, poserr = 0.f, velerr = -rel;
-                if (p > 0.f) velerr -= p / hdt; else poserr = -p * erp / hdt;
+                if (p > 0.f) velerr -= p * inv_h; else poserr = -p * erp * inv_h;
                 rhs = (poserr + velerr) * invD;
                 hi = 1e10f;
             } else rhs = -rel * invD;
         }
-        const float omc = 1.f - cfmt;
-        // Delassus row, scaled by this row's 1/(D + cfm):  A[r][s] = (w_r . z_s) * invD_r ; the solver works on
+        // Delassus row, scaled by this row's 1/(D + cfm):  A[r][s] = (z_r D^-1 . z_s) * invD_r ; the solver works on
         // c_r = lam_r (1 - cfm_r) + rhs_r - (J_r dv) invD_r, so the diagonal carries the extra -(1 - cfm_r).
-        // The row stays in REGISTERS (every solver index is a compile-time constant): slots are visited in groups of
-        // four -- normals {0-3, 4-7}, friction {8-11, ...}, limits {24-27, 28-31} -- and groups without a live row are skipped.
+        // The row stays in REGISTERS (every solver index is a compile-time constant).  Slots are visited in groups of
+        // four -- normals {0-3, 4-7}, friction {8-11, ...}, limits {24-27, 28-31} -- and groups without a live row are
+        // skipped (warp-uniform).  The dof dimension is the OUTER loop, four dofs at a time: one LDS.128 of the lane's own
+        // row and of 1/D, then one broadcast LDS.128 + 4 FFMA per live slot.
+        unsigned gmask = 0;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const bool on = g < 2 ? nc > 4 * g : (g < 6 ? nc > 2 * (g - 2) : nl > 4 * (g - 6));
+            gmask |= on ? 1u << g : 0u;
+        }
         float Ar[32];
 #pragma unroll
         for (int k = 0; k < 32; k++) Ar[k] = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < 8; g++) {
-            const bool on = g < 2 ? nc > 4 * g : (g < 6 ? nc > 2 * (g - 2) : nl > 4 * (g - 6));
-            if (!on) continue;
-            float a4[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const int sl = 4 * g + jj;
-                const float4* Zs = reinterpret_cast<const float4*>(Z + sl * ZS);
-                float a = 0.f;
-#pragma unroll
-                for (int j = 0; j < ZS / 4; j++) {
-                    float4 v = Zs[j];
-                    a = fmaf(z[4 * j], v.x, a); a = fmaf(z[4 * j + 1], v.y, a); a = fmaf(z[4 * j + 2], v.z, a);
-                    if (4 * j + 3 < ND) a = fmaf(z[4 * j + 3], v.w, a);
-                }
-                a4[jj] = a * invD - (sl == r && rtype >= 0 ? (rtype == 1 ? -cfmt : omc) : 0.f);
-            }
-            switch (g) {
-                case 0: Ar[0] = a4[0]; Ar[1] = a4[1]; Ar[2] = a4[2]; Ar[3] = a4[3]; break;
-                case 1: Ar[4] = a4[0]; Ar[5] = a4[1]; Ar[6] = a4[2]; Ar[7] = a4[3]; break;
-                case 2: Ar[8] = a4[0]; Ar[9] = a4[1]; Ar[10] = a4[2]; Ar[11] = a4[3]; break;
-                case 3: Ar[12] = a4[0]; Ar[13] = a4[1]; Ar[14] = a4[2]; Ar[15] = a4[3]; break;
-                case 4: Ar[16] = a4[0]; Ar[17] = a4[1]; Ar[18] = a4[2]; Ar[19] = a4[3]; break;
-                case 5: Ar[20] = a4[0]; Ar[21] = a4[1]; Ar[22] = a4[2]; Ar[23] = a4[3]; break;
-                case 6: Ar[24] = a4[0]; Ar[25] = a4[1]; Ar[26] = a4[2]; Ar[27] = a4[3]; break;
-                default: Ar[28] = a4[0]; Ar[29] = a4[1]; Ar[30] = a4[2]; Ar[31] = a4[3]; break;
-            }
-        }
-        __syncwarp();
-        // overwrite Z with w for the final velocity update
         {
-            float4* Zr = reinterpret_cast<float4*>(Z + r * ZS);
+            const float4* Z4 = reinterpret_cast<const float4*>(Z);
+            const float4* D4 = reinterpret_cast<const float4*>(W.dinv);
+#pragma unroll 1
+            for (int j = 0; j < ZS / 4; j++) {
+                const float4 o = Z4[r * (ZS / 4) + j], d = D4[j];
+                const float w0 = o.x * d.x, w1 = o.y * d.y, w2 = o.z * d.z, w3 = o.w * d.w;
 #pragma unroll
-            for (int j = 0; j < ZS / 4; j++) Zr[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+                for (int g = 0; g < 8; g++) {
+                    if ((gmask >> g) & 1u) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) {
+                            const float4 v = Z4[(4 * g + jj) * (ZS / 4) + j];
+                            float a = Ar[4 * g + jj];
+                            a = fmaf(w0, v.x, a); a = fmaf(w1, v.y, a); a = fmaf(w2, v.z, a); a = fmaf(w3, v.w, a);
+                            Ar[4 * g + jj] = a;
+                        }
+                    }
+                }
+            }
+            const float dself = rtype == 1 ? -cfmt : 1.f - cfmt;
+#pragma unroll
+            for (int k = 0; k < 32; k++) Ar[k] = Ar[k] * invD - ((k == r && rtype >= 0) ? dself : 0.f);
         }
         if (DIAG && dbg) {
             dbg[DBG_ROWS + 0] = (float)nl; dbg[DBG_ROWS + 1] = (float)nc;
@@ -1128,23 +1142,26 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
                 if (nc > k) { SS_NORMAL_STEP(k); SS_NORMAL_STEP(k + 1); }
             float ln = shfl(lam, nsrc);
             if (isfric) { bool live = ln > 0.f; hi_c = live ? mu * ln : lam; lo_c = live ? -hi_c : lam; }
+            // friction rows of a contact that does not push are no-ops (bounds pinned to the current impulse; Bullet skips
+            // them too: `if (totalImpulse > 0)` in solveSingleIteration): skip the pair's four row steps, warp-uniformly
+            const unsigned pushing = __ballot_sync(FULL, lam > 0.f) & ((1u << MAXC) - 1u);
 #pragma unroll
             for (int k = 0; k < MAXC; k += 2)
-                if (nc > k) {
+                if ((pushing >> k) & 3u) {
                     SS_ROW_STEP(MAXC + 2 * k); SS_ROW_STEP(MAXC + 2 * k + 1); SS_ROW_STEP(MAXC + 2 * k + 2); SS_ROW_STEP(MAXC + 2 * k + 3);
                 }
         }
 #undef SS_ROW_STEP
 #undef SS_NORMAL_STEP
         if (DIAG && dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
-        // ---- velocity update: dv = L^-T sum_r w_r lam_r ----
-        __syncwarp();        // the w rows written above (lane = row) are read below with lane = dof
+        // ---- velocity update: dv = L^-T D^-1 sum_r z_r lam_r ----
+        __syncwarp();
         float u = 0.f;
         auto gather = [&](int s0, int s1) {
             for (int s = s0; s < s1; s++) { float ls = shfl(lam, s); if (lane < ND) u = fmaf(Z[s * ZS + lane], ls, u); }
         };
         gather(0, nc); gather(MAXC, MAXC + 2 * nc); gather(3 * MAXC, 3 * MAXC + nl);
-        dv = solve_lt(W, u, lane);
+        dv = solve_lt(W, u * W.dinv[lane], lane);
         // warm-start cache for the next substep: lanes 0..7 the contact ids, lanes 8..15 their normal impulses
         float lw = shfl(lam, (lane - MAXC) & (MAXC - 1));
         newwarm = -1.f;

@@ -226,7 +226,7 @@ __device__ __forceinline__ void calc_state(const DevModel& M, WarpSmem& W, const
     __syncwarp();
     if (lane < 6) W.vec[lane] = clip5(lane == 0 ? more[0] : lane == 1 ? more[1] : lane == 2 ? more[2] : lane == 3 ? more[3] : lane == 4 ? more[4] : more[5]);
     else if (lane < ND) { W.vec[lane] = clip5(ang); W.vec[21 + lane] = clip5(spd); }
-    else if (lane < ND + 2) W.vec[48 + lane - ND] = clip5(E.feet_contact[lane - ND]);
+    else if (lane < ND + 2) W.vec[48 + lane - ND] = clip5(lane == ND ? E.feet_contact[0] : E.feet_contact[1]);
     __syncwarp();
     bool ok = true;
     if (lane < 25) ok = isfinite(W.vec[lane]) && isfinite(W.vec[25 + lane]);
@@ -510,8 +510,11 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 
 // DIAG = per-substep trace / debug dump requested (parity tests): a second instantiation, so that the production kernel
 // carries neither the code nor the registers of the probes.
+// S is __grid_constant__: its address is handed to the out-of-line reset path, and taking the address of a plain by-value
+// parameter makes every thread copy the whole struct to its local-memory frame in the prologue (8 STL.128 per thread
+// = 33 MB of DRAM writes per 8192-env launch once the dirty lines are evicted: profiles/r01l traffic).
 template <bool DIAG>
-__global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel* gm, DevState S, const float* __restrict__ act,
+__global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel* gm, const __grid_constant__ DevState S, const float* __restrict__ act,
                                                          float* __restrict__ obs, float* __restrict__ rew,
                                                          uint8_t* __restrict__ done, uint8_t* __restrict__ timeout,
                                                          float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int physics,
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
         setup_stones(M, S, W, e, E, lane);
         // the double-precision base position is not needed inside the substeps (they integrate the displacement dpos):
         // park it in shared memory so that it does not hold six registers through the solver
-        if (lane < 3) W.parked[lane] = E.pos[lane];
+        if (lane < 3) W.parked[lane] = lane == 0 ? E.pos[0] : (lane == 1 ? E.pos[1] : E.pos[2]);     // (no dynamic index: E stays in registers)
         float dpos[3] = { 0.f, 0.f, 0.f };
         for (int s = 0; s < M.n_substeps; s++) {
 #if SS_SYNC
@@ -656,7 +659,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     if (d) { __syncwarp(); env_reset_from_memory(&M, &S, &W, e, o, lane); }         // envs_utils.py:646-649
 }
 
-__global__ void __launch_bounds__(BLOCK) env_reset_kernel(const DevModel* gm, DevState S, float* __restrict__ obs) {
+__global__ void __launch_bounds__(BLOCK) env_reset_kernel(const DevModel* gm, const __grid_constant__ DevState S, float* __restrict__ obs) {
     BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
     stage_model(B, gm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

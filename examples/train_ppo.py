@@ -206,7 +206,12 @@ def main():
         if args.use_curriculum and n_ep > 0 and mean_r > 1000 and curriculum <= 4:      # train.py:503-506
             curriculum += 1
             envs.update_curriculum(curriculum)
-        if args.minutes and time.time() - t_start > args.minutes * 60:
+        stop = bool(args.minutes and time.time() - t_start > args.minutes * 60)
+        if distributed:        # rank 0's clock decides for everybody: a rank that left alone would hang the others' collectives
+            flag = torch.tensor([1.0 if stop else 0.0], device=dev)
+            torch.distributed.broadcast(flag, src=0)
+            stop = bool(flag.item())
+        if stop:
             break
     envs.close()
     if distributed:

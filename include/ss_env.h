@@ -31,6 +31,7 @@ extern "C" {
 #define SS_NWARM 16      /* warm-start cache: ids of the last substep's <= 8 contacts (-1 = none), then their normal impulses */
 #define SS_NSCAL 16      /* doubles per env in ss_state_view.scalars                              */
 #define SS_NINT 8        /* int32 per env in ss_state_view.ints                                   */
+#define SS_NEV 10        /* int32 per env and substep in the discrete-event trace (ss_substep_events)   */
 #define SS_MT_WORDS 625  /* MT19937: 624 state words + position                                   */
 
 /* scalars[]: */
@@ -126,6 +127,12 @@ int ss_set_state(ss_env* env, const ss_state_view* view);
  * qd_host [4,N,27] doubles.  Must be enabled first (costs 1.76 KB/env of extra stores per step). */
 int ss_enable_substep_trace(ss_env* env, int32_t on);
 int ss_substep_trace(ss_env* env, double* q_host, double* qd_host);
+/* The DISCRETE decisions each of those substeps took: ev_host [4,N,SS_NEV] int32 = bit j set: hinge j got a lower-limit row
+ * (btMultiBodyJointLimitConstraint: q - lo <= 0), same for the upper limit (bit 30 of that word: the max_coord_vel safety
+ * clamp engaged in this substep), then the ids of the <= 8 contact points that entered the solver (-1 = none).  A limit row or a contact point exists or not, so fp32 rounding can flip such a decision
+ * where the fp64 reference sits within rounding of the threshold; the parity tests compare trajectories conditional on
+ * equal decisions and account for every flip.  Needs ss_enable_substep_trace. */
+int ss_substep_events(ss_env* env, int32_t* ev_host);
 
 /* Stand-alone articulated-body forward-dynamics substep (no contacts, no limits): the
  * `aba_substep` kernel boundary of SURVEY 8(d) -- reads q [N,28], qd [N,27], tau [N,21] (f32, device),
@@ -137,6 +144,21 @@ int ss_aba_substep(ss_env* env, float* q_dev, float* qd_dev, const float* tau_de
 int ss_gae(const float* rewards_dev, const float* value_preds_dev, const float* masks_dev,
            const float* bad_masks_dev, float* returns_dev, int32_t T, int32_t N, float gamma,
            float gae_lambda, void* stream);
+
+/* Sticky error flags of the device entry points (synchronises).  Bit 0 (SS_FLAG_BAD_ACTION): a non-finite action reached
+ * ss_step.  The reference asserts inside every worker's step() (robots.py:290); ss_step_host does the same check on the host
+ * and refuses the batch, but ss_step is stream-ordered and cannot raise: the env steps such an action as all-zero (state
+ * and reward stay finite) and sets the flag -- check it once per rollout (steppingstone_b200.collector does). */
+#define SS_FLAG_BAD_ACTION 1
+int ss_error_flags(ss_env* env, int32_t* flags_out, int32_t clear);
+
+/* Golden-tape probe: one step() with the PHYSICS REPLACED by the state the caller has just injected with ss_set_state
+ * (q, qd and the two foot-contact flags scalars[SS_S_CACHE_CONTACT0..1]) -- everything after pybullet.stepSimulation runs:
+ * calc_state, calc_env_state, rewards, TimeLimit / Monitor bookkeeping, auto-reset.  The reference-generated fixtures
+ * (tests/golden/ *.npz, tools/gen_golden.py) replay through this entry point on the GPU
+ * (tests/test_gpu_parity.py::test_gpu_replays_reference_goldens).  Same buffers as ss_step. */
+int ss_step_injected(ss_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
+                     uint8_t* timeout_dev, float* ep_ret_dev, int32_t* ep_len_dev, void* stream);
 
 /* Parity probes (tests only; no reference analogue).
  * ss_env_post: calc_state + calc_env_state on the CURRENT state without stepping the physics

@@ -156,6 +156,11 @@ class Oracle:
         assert self.lib.sso_substep_trace(self.h, _ptr(q), _ptr(qd)) == 0
         return q, qd
 
+    def substep_events(self):
+        ev = np.zeros((4, self.n, 10), np.int32)
+        assert self.lib.sso_substep_events(self.h, _ptr(ev)) == 0
+        return ev
+
     def aba_substep(self, q, qd, tau):
         q = np.ascontiguousarray(q, dtype=np.float64).copy()
         qd = np.ascontiguousarray(qd, dtype=np.float64).copy()

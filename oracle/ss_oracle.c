@@ -173,6 +173,7 @@ typedef struct {
     int next_step, reached_count, mirrored, elapsed, ep_len, update_terrain, phantom_idx, started;
     mt_t rng, grng;
     double trace_q[4][SS_NQ], trace_qd[4][ND];
+    int32_t ev_cur[SS_NEV], trace_ev[4][SS_NEV];   /* discrete decisions of each substep: limit rows (lo / hi hinge masks), contact ids */
     /* scratch shared between calc_* functions of one step */
     double body_rpy[3], joint_speeds[NJ], joint_angles[NJ], robot_state[50];
     int joints_at_limit, target_reached, done;
@@ -524,8 +525,13 @@ static void plane_space(const double* n, double* p, double* q) {
  * ---------------------------------------------------------------------------------------------- */
 typedef struct { double J[ND], W[ND], invD, rhs, cfm, lo, hi, lam, mu; int normal; } row_t;
 
-static void clamp_vel(const ss_params* P, double* gv) {
-    for (int k = 0; k < ND; k++) { if (gv[k] > P->max_coord_vel) gv[k] = P->max_coord_vel; if (gv[k] < -P->max_coord_vel) gv[k] = -P->max_coord_vel; }
+static int clamp_vel(const ss_params* P, double* gv) {      /* returns 1 if the clamp engaged */
+    int hit = 0;
+    for (int k = 0; k < ND; k++) {
+        if (gv[k] > P->max_coord_vel) { gv[k] = P->max_coord_vel; hit = 1; }
+        if (gv[k] < -P->max_coord_vel) { gv[k] = -P->max_coord_vel; hit = 1; }
+    }
+    return hit;
 }
 static void pack_vel(const env_t* e, double* gv) { memcpy(gv, e->w, 24); memcpy(gv + 3, e->v, 24); memcpy(gv + 6, e->qdj, NJ * 8); }
 static void unpack_vel(env_t* e, const double* gv) { memcpy(e->w, gv, 24); memcpy(e->v, gv + 3, 24); memcpy(e->qdj, gv + 6, NJ * 8); }
@@ -560,7 +566,7 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
     forward_dynamics(M, &K, &A, e, tau, P->gravity, acc);
     pack_vel(e, gv);
     for (int k = 0; k < ND; k++) gv[k] += h * acc[k];
-    clamp_vel(P, gv);
+    int clamped = clamp_vel(P, gv);
 
     /* ---- constraint rows: violated hinge limits, then contact normals, then 2 friction rows each ---- */
     row_t rows[MAXR]; int nl = 0;
@@ -625,6 +631,11 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
         }
     }
     int nr = nl + 3 * nc;
+    /* the substep's discrete decisions (parity probe: sso_substep_events) */
+    e->ev_cur[0] = e->ev_cur[1] = 0;
+    for (int r = 0; r < nl; r++) for (int j = 0; j < NJ; j++) if (rows[r].J[6 + j] != 0) e->ev_cur[rows[r].J[6 + j] > 0 ? 0 : 1] |= 1 << j;
+    for (int c = 0; c < MAXC; c++) e->ev_cur[2 + c] = c < nc ? con[c].id : -1;
+    if (clamped) e->ev_cur[1] |= 1 << 30;           /* the max_coord_vel safety clamp engaged (before the solve) */
     if (nr > 0) {
         double dv[ND]; memset(dv, 0, sizeof dv);
         for (int r = 0; r < nr; r++) if (rows[r].lam != 0) for (int k = 0; k < ND; k++) dv[k] += rows[r].W[k] * rows[r].lam;
@@ -648,7 +659,7 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
             }
         }
         for (int k = 0; k < ND; k++) gv[k] += dv[k];
-        clamp_vel(P, gv);
+        if (clamp_vel(P, gv)) e->ev_cur[1] |= 1 << 30;    /* ... or after it */
     }
     for (int w = 0; w < MAXC; w++) { e->warm[w] = -1; e->warm[MAXC + w] = 0; }
     for (int c = 0; c < nc; c++) { e->warm[c] = con[c].id; e->warm[MAXC + c] = rows[nl + c].lam; }
@@ -920,7 +931,10 @@ static void env_reset(const struct sso_env* S, env_t* e, float* obs) {
     calc_potential(P, e);
     write_obs(e, obs);
     e->phantom_idx = 0;          /* walker3d_envs.py:859-862: phantom.reset draws from the robot stream, see above */
-    e->elapsed = 0; e->ep_ret = 0; e->ep_len = 0; e->update_terrain = 0; e->started = 1;
+    /* update_terrain is NOT touched: the reference's reset() (walker3d_envs.py:812-867, mike.py:333-388) leaves the flag of
+     * the terminal step standing, so a following update_sample_prob / create_temp_states acts on the freshly reset env when
+     * the episode ended on a stone advance (golden: mike_ghost_sampleprob_at_done) */
+    e->elapsed = 0; e->ep_ret = 0; e->ep_len = 0; e->started = 1;
 }
 
 /* actuator_mode 0: the torque the env applies, tau_max * clip(a), held over the control step (robots.py:289-293);
@@ -952,6 +966,7 @@ static void env_step(const struct sso_env* S, env_t* e, const float* a, float* o
             if (s < 4) {
                 memcpy(e->trace_q[s], e->pos, 24); memcpy(e->trace_q[s] + 3, e->quat, 32); memcpy(e->trace_q[s] + 7, e->qj, NJ * 8);
                 pack_vel(e, e->trace_qd[s]);
+                memcpy(e->trace_ev[s], e->ev_cur, sizeof e->ev_cur);
             }
         }
     }
@@ -1172,6 +1187,11 @@ int sso_substep_trace(sso_env* S, double* q, double* qd) {
         memcpy(q + ((size_t)s * S->n + i) * SS_NQ, S->e[i].trace_q[s], SS_NQ * 8);
         memcpy(qd + ((size_t)s * S->n + i) * ND, S->e[i].trace_qd[s], ND * 8);
     }
+    return 0;
+}
+
+int sso_substep_events(sso_env* S, int32_t* ev) {
+    for (int s = 0; s < 4; s++) for (int i = 0; i < S->n; i++) memcpy(ev + ((size_t)s * S->n + i) * SS_NEV, S->e[i].trace_ev[s], SS_NEV * 4);
     return 0;
 }
 

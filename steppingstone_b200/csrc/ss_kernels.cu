@@ -466,7 +466,9 @@ __device__ __forceinline__ void env_reset(const DevModel& M, const DevState& S, 
     double dist; E.potential = calc_potential(M, E, dist);
     write_obs(W, E, obs, lane);
     E.phantom_idx = 0;            // walker3d_envs.py:859-862: the phantoms draw from the robot stream (visual only)
-    E.elapsed = 0; E.ep_ret = 0; E.ep_len = 0; E.update_terrain = 0; E.started = 1;
+    // update_terrain keeps the terminal step's value: the reference's reset() never touches it (walker3d_envs.py:812-867,
+    // mike.py:333-388), so update_sample_prob / create_temp_states right after a done-and-advance step act on the reset env
+    E.elapsed = 0; E.ep_ret = 0; E.ep_len = 0; E.started = 1;
 }
 
 // Cold path, one out-of-line copy shared by the step and reset kernels: reload the env from memory, reset, store.
@@ -542,6 +544,10 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     Env E; env_load_phys(S, e, lane, E);
     float a_in = 0.f;
     if (lane >= 6 && lane < ND) a_in = act[(size_t)e * NJ + lane - 6];
+    // robots.py:290 `assert np.isfinite(a).all()`: the host-buffer entry point refuses such a batch; on the device path
+    // there is nobody to raise to, so the env treats the whole action as zero (a NaN would otherwise clamp to -1 = full
+    // negative torque and poison reward, GAE and the update) and raises the sticky flag ss_error_flags reports.
+    if (__any_sync(FULL, !isfinite(a_in))) { a_in = 0.f; if (lane == 0 && !ghost) atomicOr(S.err, 1); }
     stage_model_wait(B);
 
     // robots.py:289-293 apply_action (torque held over the control step) + MJCF joint damping torque.
@@ -561,7 +567,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
         if (M.actuator_mode == 2) { W.pd[0][lane] = x; W.pd[1][lane] = damp0; }
     }
     int cflags = -1;
-    if (physics) {
+    if (physics == 1) {      // 0: env logic only (ss_env_post); 2: the wrappers too, physics replaced by the injected state (ss_step_injected)
         setup_stones(M, S, W, e, E, lane);
         // the double-precision base position is not needed inside the substeps (they integrate the displacement dpos):
         // park it in shared memory so that it does not hold six registers through the solver
@@ -577,7 +583,21 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
                 tau = M.pd_p[j] * (W.pd[0][lane] - 2.f * (E.q_dof - 0.5f * (lo + hi)) / (hi - lo)) - M.pd_d[j] * E.v_dof - W.pd[1][lane];
             }
             float* dbg = (DIAG && S.dbg && s == M.n_substeps - 1) ? S.dbg + (size_t)e * DBG_FLOATS : nullptr;
-            cflags = substep_warp<DIAG>(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg);
+            unsigned ev_lo = 0, ev_hi = 0;
+            if (DIAG && S.trace_ev) {            // the limit rows this substep is about to create (same test as substep_warp)
+                int lv = 0;
+                if (lane >= 6 && lane < ND) lv = (E.q_dof - M.q_lo[lane - 6] <= 0.f) ? 1 : ((M.q_hi[lane - 6] - E.q_dof <= 0.f) ? 2 : 0);
+                const unsigned any = __ballot_sync(FULL, lv != 0);
+                const bool kept = lv != 0 && __popc(any & ((1u << lane) - 1u)) < MAXL;
+                ev_lo = __ballot_sync(FULL, kept && lv == 1) >> 6; ev_hi = __ballot_sync(FULL, kept && lv == 2) >> 6;
+            }
+            bool clamp_hit = false;
+            cflags = substep_warp<DIAG>(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg, DIAG ? &clamp_hit : nullptr);
+            if (DIAG && S.trace_ev && s < 4 && !ghost) {
+                int* ev = S.trace_ev + ((size_t)s * S.n + e) * SS_NEV;
+                if (lane < MAXC) ev[2 + lane] = (int)E.warm;           // contact ids of this substep (-1 = none)
+                if (lane == 0) { ev[0] = (int)ev_lo; ev[1] = (int)(ev_hi | (clamp_hit ? 1u << 30 : 0u)); }   // bit 30: max_coord_vel clamp engaged
+            }
             if (DIAG && S.trace_q && s < 4 && !ghost) {
                 double* tq = S.trace_q + ((size_t)s * S.n + e) * SS_NQ;
                 double* tv = S.trace_qd + ((size_t)s * S.n + e) * ND;
@@ -610,11 +630,12 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     float posture = 0.f;
     if (!(-0.2f < rpy[1] && rpy[1] < 0.4f)) posture = fabsf(rpy[1]);
     if (!(-0.4f < rpy[0] && rpy[0] < 0.4f)) posture += fabsf(rpy[0]);
-    float m1 = 0.f, m2 = 0.f;
+    float m1 = 0.f, m2 = 0.f, a_again = 0.f;
     if (lane >= 6 && lane < ND) {                                                               // unclipped action (q5)
-        const float a_again = act[(size_t)e * NJ + lane - 6];      // re-read (L1/L2 hit): keeps a register free through the physics
-        m1 = fabsf(a_again * 0.1f * E.v_dof); m2 = a_again * a_again;
+        a_again = act[(size_t)e * NJ + lane - 6];      // re-read (L1/L2 hit): keeps a register free through the physics
     }
+    if (__any_sync(FULL, !isfinite(a_again))) a_again = 0.f;           // non-finite action: stepped as zero (see the top)
+    m1 = fabsf(a_again * 0.1f * E.v_dof); m2 = a_again * a_again;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) { m1 += __shfl_xor_sync(FULL, m1, off); m2 += __shfl_xor_sync(FULL, m2, off); }
     float energy = M.electricity_cost * (m1 / NJ) + M.stall_torque_cost * (m2 / NJ);
@@ -1044,6 +1065,7 @@ static int create_device_state(ss_env* E, const ss_model* model, const uint32_t*
     CK(cudaMalloc(&S.ints, N * SS_NINT * sizeof(int)));
     CK(cudaMalloc(&S.mt, N * 2 * SS_MT_WORDS * sizeof(uint32_t)));
     CK(cudaMalloc(&S.perm, N * sizeof(int)));
+    CK(cudaMalloc(&S.err, sizeof(int))); CK(cudaMemset(S.err, 0, sizeof(int)));
     CK(cudaMalloc(&E->sort_keys, N)); CK(cudaMalloc(&E->sort_bins, SS_PIPE * SORT_SLOT * sizeof(int)));
     { std::vector<int> id(N); for (size_t i = 0; i < N; i++) id[i] = (int)i; CK(cudaMemcpy(S.perm, id.data(), N * sizeof(int), cudaMemcpyHostToDevice)); }
     CK(cudaMalloc(&E->cdf, (size_t)SS_GRID_CELLS * sizeof(double)));
@@ -1091,7 +1113,7 @@ void ss_destroy(ss_env* E) {
     cudaDeviceSynchronize();
     DevState& S = E->S;
     cudaFree(E->dm); cudaFree(S.pos); cudaFree(S.sv); cudaFree(S.warm); cudaFree(S.terrain); cudaFree(S.plank);
-    cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(S.perm); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.dbg);
+    cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(S.perm); cudaFree(S.err); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.trace_ev); cudaFree(S.dbg);
     cudaFreeHost(E->h_act); cudaFreeHost(E->h_rec); cudaFree(E->d_act); cudaFree(E->d_rec);
     for (int k = 0; k < SS_PIPE; k++) if (E->pipe[k]) cudaStreamDestroy(E->pipe[k]);
     cudaFree(E->ts_base); cudaFree(E->ts_ctx); cudaFree(E->sort_keys); cudaFree(E->sort_bins);
@@ -1111,7 +1133,7 @@ int ss_reset_all(ss_env* E, float* obs_dev, void* stream) {
 static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el,
                        cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr, int slot = 0) {
     if (e_end < 0) e_end = E->n;
-    if (physics && e_end - e_begin >= 4 * WARPS_PER_BLOCK) {
+    if (physics == 1 && e_end - e_begin >= 4 * WARPS_PER_BLOCK) {
         int* bins = E->sort_bins + SORT_SLOT * slot;
         const int nb = (e_end - e_begin + SORT_THREADS - 1) / SORT_THREADS;
         CK(cudaMemsetAsync(bins, 0, SORT_SLOT * sizeof(int), st));
@@ -1119,7 +1141,7 @@ static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint
         sort_scatter_kernel<<<nb, SORT_THREADS, 0, st>>>(E->S, E->sort_keys, bins, e_begin, e_end);
         E->launches += 2;
     }
-    if (E->S.dbg || E->S.trace_q)
+    if (E->S.dbg || E->S.trace_q || E->S.trace_ev)
         env_step_kernel<true><<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
                                                                                  e_begin, e_end, packed);
     else
@@ -1136,6 +1158,14 @@ int ss_step(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev, uin
         return fail(SS_ERR_ARG, "ss_step: null buffer");
     CK(cudaSetDevice(E->device));
     return launch_step(E, act_dev, obs_dev, rew_dev, done_dev, timeout_dev, ep_ret_dev, ep_len_dev, (cudaStream_t)stream, 1);
+}
+
+int ss_step_injected(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, uint8_t* timeout_dev,
+                     float* ep_ret_dev, int32_t* ep_len_dev, void* stream) {
+    if (!E || !act_dev || !obs_dev || !rew_dev || !done_dev || !timeout_dev || !ep_ret_dev || !ep_len_dev)
+        return fail(SS_ERR_ARG, "ss_step_injected: null buffer");
+    CK(cudaSetDevice(E->device));
+    return launch_step(E, act_dev, obs_dev, rew_dev, done_dev, timeout_dev, ep_ret_dev, ep_len_dev, (cudaStream_t)stream, 2);
 }
 
 int ss_env_post(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream) {
@@ -1228,13 +1258,17 @@ int ss_reset_host(ss_env* E, float* obs) {
 int ss_set_sample_cdf(ss_env* E, const double* cdf, int32_t n_cells, int32_t apply_now, void* stream) {
     if (!E || !cdf || n_cells != SS_GRID_CELLS) return fail(SS_ERR_ARG, "ss_set_sample_cdf: table must have 11^5 cells");
     CK(cudaSetDevice(E->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    // stream == NULL (host-buffer mode): the library's own stream, synchronised before returning.  The legacy default
+    // stream would NOT do: ss_step_host works on cudaStreamNonBlocking streams, which do not wait for it, so the re-sample
+    // (it writes terrain, planks and RNG state) could still be running when the next step starts.
+    cudaStream_t st = stream ? (cudaStream_t)stream : E->own;
     CK(cudaStreamSynchronize(st));
     CK(cudaMemcpy(E->cdf, cdf, (size_t)n_cells * 8, cudaMemcpyHostToDevice));
     if (apply_now) {
         resample_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S);
         E->launches++;
         CK(cudaGetLastError());
+        if (!stream) CK(cudaStreamSynchronize(st));
     }
     return SS_OK;
 }
@@ -1350,8 +1384,9 @@ int ss_enable_substep_trace(ss_env* E, int32_t on) {
     if (on && !S.trace_q) {
         CK(cudaMalloc(&S.trace_q, (size_t)4 * E->n * SS_NQ * 8)); CK(cudaMalloc(&S.trace_qd, (size_t)4 * E->n * ND * 8));
         CK(cudaMemset(S.trace_q, 0, (size_t)4 * E->n * SS_NQ * 8)); CK(cudaMemset(S.trace_qd, 0, (size_t)4 * E->n * ND * 8));
+        CK(cudaMalloc(&S.trace_ev, (size_t)4 * E->n * SS_NEV * 4)); CK(cudaMemset(S.trace_ev, 0xff, (size_t)4 * E->n * SS_NEV * 4));
     } else if (!on && S.trace_q) {
-        cudaFree(S.trace_q); cudaFree(S.trace_qd); S.trace_q = S.trace_qd = nullptr;
+        cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.trace_ev); S.trace_q = S.trace_qd = nullptr; S.trace_ev = nullptr;
     }
     return SS_OK;
 }
@@ -1363,6 +1398,15 @@ int ss_substep_trace(ss_env* E, double* q, double* qd) {
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(q, E->S.trace_q, (size_t)4 * E->n * SS_NQ * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(qd, E->S.trace_qd, (size_t)4 * E->n * ND * 8, cudaMemcpyDeviceToHost));
+    return SS_OK;
+}
+
+int ss_substep_events(ss_env* E, int32_t* ev) {
+    if (!E || !ev) return fail(SS_ERR_ARG, "ss_substep_events: bad argument");
+    if (!E->S.trace_ev) return fail(SS_ERR_STATE, "ss_substep_events: tracing is not enabled");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ev, E->S.trace_ev, (size_t)4 * E->n * SS_NEV * 4, cudaMemcpyDeviceToHost));
     return SS_OK;
 }
 
@@ -1399,6 +1443,15 @@ int ss_gae(const float* rewards, const float* values, const float* masks, const 
     if (!rewards || !values || !masks || !bad_masks || !returns || T <= 0 || N <= 0) return fail(SS_ERR_ARG, "ss_gae: bad argument");
     gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, masks, bad_masks, returns, T, N, gamma, lam);
     CK(cudaGetLastError());
+    return SS_OK;
+}
+
+int ss_error_flags(ss_env* E, int32_t* flags, int32_t clear) {
+    if (!E || !flags) return fail(SS_ERR_ARG, "ss_error_flags: bad argument");
+    CK(cudaSetDevice(E->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(flags, E->S.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (clear) CK(cudaMemset(E->S.err, 0, sizeof(int)));
     return SS_OK;
 }
 

@@ -53,12 +53,27 @@ def build_native(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("libss_b200.so is missing or stale and nvcc was not found to build it")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + _sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    # Several ranks of one torchrun job may find the library stale at the same moment: build under an exclusive file lock,
+    # into a temporary file that is renamed into place (a reader never sees a half-written .so), and re-check after
+    # acquiring the lock so that only the first rank compiles.
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-I", CSRC, "-o", tmp] + _sources()
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -71,6 +86,7 @@ _SIGNATURES = {
     "ss_destroy": (None, [_P]),
     "ss_reset_all": (ctypes.c_int, [_P, _P, _P]),
     "ss_step": (ctypes.c_int, [_P] * 9),
+    "ss_step_injected": (ctypes.c_int, [_P] * 9),
     "ss_step_host": (ctypes.c_int, [_P] * 8),
     "ss_reset_host": (ctypes.c_int, [_P, _P]),
     "ss_set_sample_cdf": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
@@ -81,6 +97,7 @@ _SIGNATURES = {
     "ss_set_state": (ctypes.c_int, [_P, _P]),
     "ss_enable_substep_trace": (ctypes.c_int, [_P, _I32]),
     "ss_substep_trace": (ctypes.c_int, [_P, _P, _P]),
+    "ss_substep_events": (ctypes.c_int, [_P, _P]),
     "ss_aba_substep": (ctypes.c_int, [_P, _P, _P, _P, _I32, _P]),
     "ss_gae": (ctypes.c_int, [_P, _P, _P, _P, _P, _I32, _I32, ctypes.c_float, ctypes.c_float, _P]),
     "ss_env_post": (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
@@ -88,6 +105,7 @@ _SIGNATURES = {
     "ss_enable_debug": (ctypes.c_int, [_P, _I32]),
     "ss_debug_read": (ctypes.c_int, [_P, _P]),
     "ss_host_timing": (ctypes.c_int, [_P, _P]),
+    "ss_error_flags": (ctypes.c_int, [_P, _P, _I32]),
     "ss_num_envs": (_I32, [_P]),
     "ss_launch_count": (ctypes.c_int64, [_P]),
     "ss_last_error": (ctypes.c_char_p, []),

@@ -88,6 +88,7 @@ class BatchedStepperEnv:
         self._pending = None
         self._no_infos = (_NO_INFO,) * self.num_envs
         self.curriculum = 0
+        self._table = None                                                  # uniform until a table is set
         N = self.num_envs
         if output == "numpy":
             self._timeout = np.zeros(N, np.uint8)
@@ -164,8 +165,16 @@ class BatchedStepperEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    def check_errors(self, clear=True):
+        """Device mode cannot raise from inside a stream-ordered ``ss_step``: a non-finite action (robots.py:290 asserts on
+        it in the reference) is stepped as zero and remembered.  Call once per rollout; raises like the reference would."""
+        flags = ctypes.c_int32(0)
+        native.check(self._lib.ss_error_flags(self._h, ctypes.byref(flags), int(clear)), "ss_error_flags")
+        assert not (flags.value & 1), "a non-finite action reached step() since the last check (robots.py:290)"
+
     # ------------------------------------------------------------------ curriculum ops (envs_utils.py:560-590)
     def _set_table(self, p, apply_now=False):
+        self._table = np.array(p, dtype=np.float64).reshape(-1)             # kept for save_state
         cdf = seeding.choice_cdf(p)
         stream = self._stream() if self.output == "torch" else None
         native.check(self._lib.ss_set_sample_cdf(self._h, cdf.ctypes.data, cdf.size, int(apply_now), stream), "ss_set_sample_cdf")
@@ -295,22 +304,77 @@ class BatchedStepperEnv:
         native.check(self._lib.ss_get_state(self._h, ctypes.byref(v)), "ss_get_state")
         return st
 
+    def _state_spec(self):
+        N = self.num_envs
+        return {"q": (np.float64, (N, native.NQ)), "qd": (np.float64, (N, native.ND)), "warm": (np.float64, (N, native.NWARM)),
+                "terrain": (np.float64, (N, self.n_steps, 6)), "plank": (np.float64, (N, self.rendered, 6)),
+                "scalars": (np.float64, (N, native.NSCAL)), "ints": (np.int32, (N, native.NINT)),
+                "mt": (np.uint32, (N, 2, native.MTW))}
+
     def set_state(self, st):
-        st = {k: (None if a is None else np.ascontiguousarray(a)) for k, a in st.items()}
-        v = native.make_view(st)
+        """Any subset of the ``get_state`` arrays.  Every array is converted to the dtype the C-ABI copies (a float32 ``q``
+        used to be memcpy'd as doubles) and its shape is checked."""
+        spec = self._state_spec()
+        out = {}
+        for k, a in st.items():
+            if a is None:
+                continue
+            if k not in spec:
+                raise KeyError("unknown state array %r (expected a subset of %s)" % (k, sorted(spec)))
+            dtype, shape = spec[k]
+            a = np.ascontiguousarray(a, dtype=dtype)
+            if a.shape != shape:
+                raise ValueError("state array %r has shape %s, expected %s" % (k, a.shape, shape))
+            out[k] = a
+        v = native.make_view(out)
         native.check(self._lib.ss_set_state(self._h, ctypes.byref(v)), "ss_set_state")
 
+    @staticmethod
+    def _npz(path):
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"
+
     def save_state(self, path):
-        """Checkpoint the whole simulator state (poses, velocities, contact cache, terrain, planks, bookkeeping, both
-        MT19937 streams of every env) to an .npz: ``load_state`` on an env built with the same arguments continues the
+        """Checkpoint the whole simulator to an .npz: poses, velocities, contact cache, terrain, planks, bookkeeping and
+        both MT19937 streams of every env, plus what lives outside those arrays -- the sampling table in force
+        (curriculum / specialist / update_sample_prob), the curriculum level, the env-parameter overrides and the robot's
+        power / PD tables.  ``load_state`` on an env built with the same (env_id, seed, num_envs, first_env) continues the
         rollout bit for bit.  The reference has no equivalent (its env state dies with the worker processes)."""
+        import json
         st = self.get_state()
-        np.savez_compressed(path, env_id=self.env_id, seed=self.seed, first_env=self.first_env, **st)
+        np.savez_compressed(self._npz(path), env_id=self.env_id, seed=self.seed, first_env=self.first_env,
+                            n_steps=self.n_steps, rendered=self.rendered, curriculum=self.curriculum,
+                            has_table=self._table is not None, table=(self._table if self._table is not None else np.zeros(0)),
+                            overrides=json.dumps(self._overrides), terrain_mode=json.dumps(self._terrain_mode),
+                            power=self._power, tau_max=self._tables["tau_max"], pd_p=self._tables["pd_p"],
+                            pd_d=self._tables["pd_d"], fake_grid=self._fake_grid, **st)
 
     def load_state(self, path):
-        with np.load(path) as z:
-            if str(z["env_id"]) != self.env_id or z["q"].shape[0] != self.num_envs:
-                raise ValueError("checkpoint is for %s x %d envs" % (z["env_id"], z["q"].shape[0]))
+        import json
+        with np.load(self._npz(path)) as z:
+            for key, mine in (("env_id", self.env_id), ("seed", self.seed), ("first_env", self.first_env),
+                              ("n_steps", self.n_steps), ("rendered", self.rendered)):
+                if key in z.files and str(z[key]) != str(mine):
+                    raise ValueError("checkpoint was written with %s = %s, this env has %s" % (key, z[key], mine))
+            if z["q"].shape[0] != self.num_envs:
+                raise ValueError("checkpoint is for %d envs, this env has %d" % (z["q"].shape[0], self.num_envs))
+            if "overrides" in z.files:                                     # (older checkpoints hold the state arrays only)
+                self._overrides = json.loads(str(z["overrides"]))
+                self._terrain_mode = json.loads(str(z["terrain_mode"]))
+                self._power = float(z["power"])
+                for k in ("tau_max", "pd_p", "pd_d"):
+                    self._tables[k] = np.array(z[k])
+                self._fake_grid = np.array(z["fake_grid"])
+                self._push_tables()
+                self._max_episode_steps = self._params.max_episode_steps
+                if bool(z["has_table"]):
+                    self._set_table(np.array(z["table"]))
+                elif self._table is not None:                              # back to the table ss_create installs: uniform
+                    cdf = (np.arange(native.GRID_CELLS, dtype=np.float64) + 1.0) / native.GRID_CELLS
+                    stream = self._stream() if self.output == "torch" else None
+                    native.check(self._lib.ss_set_sample_cdf(self._h, cdf.ctypes.data, cdf.size, 0, stream), "ss_set_sample_cdf")
+                    self._table = None
+                self.curriculum = int(z["curriculum"])
             self.set_state({k: z[k] for k in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt")})
 
     def enable_substep_trace(self, on=True):
@@ -322,6 +386,12 @@ class BatchedStepperEnv:
         native.check(self._lib.ss_substep_trace(self._h, q.ctypes.data, qd.ctypes.data), "ss_substep_trace")
         return q, qd
 
+    def substep_events(self):
+        """[4, N, 10] int32: lower / upper limit-row hinge masks and the <= 8 contact ids of each substep of the last step."""
+        ev = np.zeros((4, self.num_envs, 10), np.int32)
+        native.check(self._lib.ss_substep_events(self._h, ev.ctypes.data), "ss_substep_events")
+        return ev
+
     def enable_debug(self, on=True):
         native.check(self._lib.ss_enable_debug(self._h, int(on)), "ss_enable_debug")
 
@@ -329,6 +399,30 @@ class BatchedStepperEnv:
         out = np.zeros((self.num_envs, self._lib.ss_debug_floats()), np.float32)
         native.check(self._lib.ss_debug_read(self._h, out.ctypes.data), "ss_debug_read")
         return out
+
+    def step_injected(self, actions, q, qd, contact):
+        """One step() with the physics replaced by a post-physics state (q [N,28], qd [N,27], foot-contact flags [N,2]):
+        everything after ``stepSimulation`` runs -- calc_state, calc_env_state, rewards, TimeLimit / Monitor, auto-reset.
+        Golden-tape probe (the reference-generated fixtures replay through it); returns numpy
+        (obs, rew, done, timeout, ep_ret, ep_len) like the oracle's ``step_injected``."""
+        torch = self._torch if self.output == "torch" else __import__("torch")
+        dev = torch.device("cuda", self.device_index)
+        N = self.num_envs
+        st = self.get_state()
+        st["q"][:] = np.asarray(q, dtype=np.float64).reshape(N, native.NQ)
+        st["qd"][:] = np.asarray(qd, dtype=np.float64).reshape(N, native.ND)
+        st["scalars"][:, 14:16] = np.asarray(contact, dtype=np.float64).reshape(N, 2)
+        self.set_state({"q": st["q"], "qd": st["qd"], "scalars": st["scalars"]})
+        a = torch.as_tensor(np.asarray(actions, dtype=np.float32).reshape(N, ACT_DIM), device=dev).contiguous()
+        obs = torch.zeros((N, OBS_DIM), dtype=torch.float32, device=dev)
+        rew = torch.zeros(N, dtype=torch.float32, device=dev)
+        done = torch.zeros(N, dtype=torch.uint8, device=dev); to = torch.zeros(N, dtype=torch.uint8, device=dev)
+        er = torch.zeros(N, dtype=torch.float32, device=dev); el = torch.zeros(N, dtype=torch.int32, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        native.check(self._lib.ss_step_injected(self._h, a.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                                to.data_ptr(), er.data_ptr(), el.data_ptr(), stream), "ss_step_injected")
+        torch.cuda.synchronize(dev)
+        return (obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), to.cpu().numpy(), er.cpu().numpy(), el.cpu().numpy())
 
     def env_post(self, actions):
         """calc_state + calc_env_state on the current state, no physics (parity probe)."""

@@ -17,7 +17,7 @@ OBS, NJ = 60, 21
 _libs = {}
 # tag -> extra compile flags: kernel variants kept verified, and the production CTA shape (20 warps per CTA: ghost warps,
 # per-substep block barrier, contact-sorted env order) next to the default one-warp-per-CTA emulation build
-VARIANTS = {"": (), "sparse": ("-DSS_SPARSE_LDL=1",), "wpb20": ("-DSS_WPB=20",)}
+VARIANTS = {"": (), "sparse": ("-DSS_SPARSE_LDL=1",), "dense": ("-DSS_SPARSE_LDL=0",), "wpb20": ("-DSS_WPB=20",)}
 
 
 def load(variant=""):
@@ -87,6 +87,23 @@ class EmuEnv:
         q = np.zeros((4, self.n, native.NQ)); qd = np.zeros((4, self.n, native.ND))
         self._ck(self.lib.ss_substep_trace(self.h, q.ctypes.data, qd.ctypes.data), "ss_substep_trace")
         return q, qd
+
+    def substep_events(self):
+        ev = np.zeros((4, self.n, 10), np.int32)
+        self._ck(self.lib.ss_substep_events(self.h, ev.ctypes.data), "ss_substep_events")
+        return ev
+
+    def step_injected(self, act, q, qd, contact):
+        st = self.get_state()
+        st["q"][:] = np.asarray(q, dtype=np.float64).reshape(self.n, native.NQ)
+        st["qd"][:] = np.asarray(qd, dtype=np.float64).reshape(self.n, native.ND)
+        st["scalars"][:, 14:16] = np.asarray(contact, dtype=np.float64).reshape(self.n, 2)
+        self.set_state({"q": st["q"], "qd": st["qd"], "scalars": st["scalars"]})
+        a = np.ascontiguousarray(act, dtype=np.float32).reshape(self.n, NJ)
+        obs = np.zeros((self.n, OBS), np.float32); rew = np.zeros(self.n, np.float32); done = np.zeros(self.n, np.uint8)
+        self._ck(self.lib.ss_step_injected(self.h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                                           self._timeout.ctypes.data, self._ep_ret.ctypes.data, self._ep_len.ctypes.data, None), "ss_step_injected")
+        return obs, rew, done, self._timeout.copy(), self._ep_ret.copy(), self._ep_len.copy()
 
     # ---- the other kernels (host arrays stand in for device buffers) ----
     def env_post(self, act):

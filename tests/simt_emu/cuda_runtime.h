@@ -174,6 +174,7 @@ static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 template <typename T> static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }   // fibers never pre-empt each other
+template <typename T> static inline T atomicOr(T* p, T v) { T old = *p; *p = old | v; return old; }
 static inline void __stcs(float4* p, float4 v) { *p = v; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }

@@ -21,83 +21,24 @@ GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
 
 def _oracle_for(g):
     from oracle.binding import Oracle
+    from parity_helpers import golden_params
     from steppingstone_b200 import model, seeding
     kind, seed = int(g["kind"]), int(g["seed"])
-    prm = {"stop_frames": int(g["stop_frames"])}
-    if int(g["time_limit"]) == 0:
-        prm["max_episode_steps"] = 1 << 30
-    M = model.make_model(kind); P = model.make_params(kind, prm)
-    o = Oracle(M, P, 1, seeding.env_streams(seed, 0, 1), seeding.aux_streams(kind, seed, 0, 1), threads=1)
-    if int(g["curriculum"]) >= 0:
-        o.set_sample_cdf(seeding.choice_cdf(seeding.curriculum_table(int(g["curriculum"]))))
-    return o
-
-
-def seeding_restore(kind):
-    from steppingstone_b200 import seeding
-    return seeding.temp_state_restore(kind)
+    M = model.make_model(kind); P = model.make_params(kind, golden_params(g))
+    return Oracle(M, P, 1, seeding.env_streams(seed, 0, 1), seeding.aux_streams(kind, seed, 0, 1), threads=1)
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 13
+    assert len(GOLDEN) >= 14
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_env_logic_matches_reference(path):
+    """The tape through the oracle (tests/parity_helpers.py::replay_golden; the GPU replays the same tapes through the
+    same function in tests/test_gpu_parity.py::test_gpu_replays_reference_goldens)."""
+    from parity_helpers import replay_golden
     g = np.load(path)
-    o = _oracle_for(g)
-    kind = int(g["kind"])
-    obs = o.reset()[0]
-    cols = np.ones(60, bool)
-    scale = np.ones(60)
-    if kind == 1:
-        scale[6:9] = 5.7e4          # Mike's locked abdomen: obs = 2(q-mid)/(hi-lo) with hi-lo = 3.5e-5 rad, in float32
-    def close(a, b, what, t):
-        err = np.abs(a.astype(np.float64) - b.astype(np.float64)) / (scale * np.maximum(1.0, np.abs(b)))
-        assert err.max() < 2e-6, "%s differs at step %d: col %d ref %r oracle %r" % (what, t, int(err.argmax()), b[int(err.argmax())], a[int(err.argmax())])
-    close(obs, g["obs0"], "reset obs", -1)
-    terr_at = list(g["terrain_at"]); terr = g["terrain"]
-    st = o.get_state()
-    assert np.abs(st["terrain"][0] - terr[0]).max() < 1e-12, "terrain after the first reset"
-    T = len(g["rew"])
-    n_ep = 0
-    ts_step = list(g["ts_step"]) if "ts_step" in g.files else []
-    sp_step = list(g["sp_step"]) if "sp_step" in g.files else []
-    for t in range(T):
-        ob, rew, done, to, er, el = o.step_injected(g["actions"][t][None], g["q"][t][None], g["qd"][t][None], g["contact"][t][None])
-        assert bool(done[0]) == bool(g["done"][t]), "done differs at step %d" % t
-        assert bool(to[0]) == bool(g["bad"][t]), "bad_transition differs at step %d" % t
-        assert abs(float(rew[0]) - g["rew"][t]) < 1e-5 * max(1.0, abs(g["rew"][t])), "reward differs at step %d: ref %r oracle %r" % (t, g["rew"][t], rew[0])
-        close(ob[0], g["obs"][t], "obs", t)
-        if t in sp_step:
-            # update_sample_prob (mike.py:827-830): new table, immediate re-sample iff this step advanced a stone
-            from steppingstone_b200 import seeding
-            o.set_sample_cdf(seeding.choice_cdf(g["sp_tables"][sp_step.index(t)].astype(np.float64)), apply_now=True)
-        if t in ts_step:
-            # value-guided sampling probes (create_temp_states_1/_2/create_temp_states, mike.py:699-753): the
-            # reference leaves walk_target at the last grid cell, so the NEXT step's reward checks that too
-            k = ts_step.index(t); variant = int(g["ts_variant"][k])
-            ts = o.create_temp_states(variant, g["ts_grid"], seeding_restore(kind))[0]
-            ref = g["ts_%d" % k]
-            if variant == 5:
-                assert np.abs(ts.astype(np.float64).sum(axis=0) - g["ts_sum_%d" % k]).max() < 2e-6 * 161051 * 5
-                ts = ts[::1009]
-            assert ts.shape == ref.shape
-            err = np.abs(ts.astype(np.float64) - ref) / (scale * np.maximum(1.0, np.abs(ref)))
-            assert err.max() < 2e-6, "temp states (variant %d) differ at step %d: %r" % (variant, t, err.max())
-        if done[0]:
-            n_ep += 1
-            assert int(el[0]) == int(g["ep_l"][t])
-            assert abs(float(er[0]) - g["ep_r"][t]) < 2e-5 * max(1.0, abs(g["ep_r"][t]))
-        if t in terr_at:
-            st = o.get_state()
-            k = terr_at.index(t)
-            assert np.abs(st["terrain"][0] - terr[k]).max() < 1e-12, "terrain_info differs after step %d" % t
-            if not done[0]:
-                assert int(st["ints"][0, 0]) == int(g["next_step"][t])
-                assert int(st["ints"][0, 1]) == int(g["reached_count"][t])
-                assert abs(st["scalars"][0, 0] - g["potential"][t]) < 1e-9 * max(1.0, abs(g["potential"][t]))
-    assert n_ep == int(g["done"].sum())
+    assert replay_golden(g, _oracle_for(g)) == len(g["rew"])
 
 
 def test_seeding_matches_numpy_randomstate():

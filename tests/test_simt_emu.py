@@ -64,6 +64,51 @@ def test_emulated_kernels_teacher_forced_substeps(kind, k_steps):
     assert worst_v < 1e-3 and worst_q < 5e-6, (worst_v, worst_q)
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_emulated_kernels_chained_control_step_is_strict(kind):
+    """One whole control step (4 chained substeps) of 96 envs from oracle states, the strict criterion of
+    tests/parity_helpers.py::chain_check: every env whose substeps took the oracle's discrete decisions (limit rows, contact
+    points, velocity clamp: ss_substep_events) is within the fp32 tolerance at every substep; every flip is accounted for."""
+    from parity_helpers import chain_check
+    n = 96
+    o = make_oracle(kind, n); g = EmuEnv(kind, n)
+    o.reset(); g.reset()
+    rng = np.random.RandomState(40 + kind)
+    for _ in range(25):
+        o.step(random_actions(rng, n))
+    g.enable_substep_trace(True)
+    for t in range(2):
+        st = o.get_state(); g.set_state(st)
+        a = random_actions(rng, n)
+        obs_o, rew_o, done_o, *_ = o.step(a); obs_g, rew_g, done_g, *_ = g.step(a)
+        strict = chain_check(o, o.substep_trace(), g.substep_trace(), o.substep_events(), g.substep_events(), st["q"],
+                             "emu kind %d step %d" % (kind, t))
+        assert strict.mean() >= 0.75
+        assert np.array_equal(done_o.astype(bool)[strict], done_g.astype(bool)[strict])
+        sel = strict & ~done_g.astype(bool)
+        cols = np.ones(60, bool); cols[6:9] = kind == 0
+        assert np.abs(obs_o - obs_g)[sel][:, cols].max() < 5e-3
+    o.close(); g.close()
+
+
+_EMU_GOLDEN = ["w3d_sim_seed8", "w3d_ghost_laststone", "w3d_walk_policy", "mike_sim_seed9", "mike_ghost_sampleprob",
+               "mike_ghost_sampleprob_at_done", "mike_ghost_timelimit", "mike_walk_policy"]
+
+
+@pytest.mark.parametrize("name", _EMU_GOLDEN)
+def test_emulated_kernels_replay_reference_goldens(name):
+    """The REFERENCE-recorded tapes (tools/gen_golden.py: the unmodified env classes inside the reference's worker wrappers)
+    through the product's kernels -- ss_set_state + ss_step_injected on the emulation -- at the oracle's tolerances
+    (observation 2e-6 relative, reward 1e-5): the env logic of the CUDA sources is pinned to the reference directly, not
+    only through the oracle.  (`-m gpu` runs all 13 tapes on the device: test_gpu_replays_reference_goldens.)"""
+    from conftest import ROOT
+    from parity_helpers import golden_params, replay_golden
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    b = EmuEnv(int(g["kind"]), 1, seed=int(g["seed"]), params=golden_params(g))
+    assert replay_golden(g, b, terrain_tol=1e-9, pot_tol=1e-7) == len(g["rew"])
+    b.close()
+
+
 @pytest.mark.parametrize("case", ["w3d_latest_shipped_terrain", "mike_latest_curriculum5"])
 def test_emulated_kernels_on_walking_states(case):
     """Per-substep parity on snapshots of a shipped policy walking the stones (feet loaded, self-contacts, hinges on
@@ -310,19 +355,20 @@ def test_shipped_policy_walks_on_the_emulated_kernels():
 
 
 @pytest.mark.parametrize("kind", KINDS)
-def test_sparse_factorisation_variant_stays_correct(kind):
-    """-DSS_SPARSE_LDL=1 (default off until it has been timed on a B200): branch-induced sparsity of the joint-space inertia,
-    H = U D U^T eliminated leaves-first, structural zeros skipped at compile time in the factorisation and the triangular
-    solves.  Same per-substep comparison against the oracle as the default build, in contact; fewer warp collectives."""
+def test_dense_factorisation_variant_stays_correct(kind):
+    """The default build factorises H = U D U^T leaves-first with the structural zeros of the kinematic tree skipped at compile
+    time (0.7207 -> 0.6942 ms per 8192-env step on a B200, profiles/r02b_variants.txt); -DSS_SPARSE_LDL=0 keeps the dense
+    row-ordered LDL^T for A/B runs.  Both get the same per-substep comparison against the oracle, in contact; the sparse one
+    needs fewer warp collectives."""
     n = 6
     prm = dict(n_substeps=1)
     o = make_oracle(kind, n, params=prm)
-    g = EmuEnv(kind, n, params=prm, variant="sparse"); d = EmuEnv(kind, n, params=prm)
+    g = EmuEnv(kind, n, params=prm); d = EmuEnv(kind, n, params=prm, variant="dense")
     o.reset(); g.reset(); d.reset()
     rng0 = np.random.RandomState(7)
     for _ in range(40):
         o.step(random_actions(rng0, n))
-    g.enable_substep_trace(True)
+    g.enable_substep_trace(True); d.enable_substep_trace(True)
     rng = np.random.RandomState(107)
     worst_v = worst_q = 0.0
     count = {}
@@ -332,13 +378,15 @@ def test_sparse_factorisation_variant_stays_correct(kind):
         o.step(a)
         for name, env in (("sparse", g), ("dense", d)):
             c0 = env.lib.simt_emu_collectives(); env.step(a); count[name] = count.get(name, 0) + env.lib.simt_emu_collectives() - c0
-        qo, qdo = o.substep_trace(); qg, qdg = g.substep_trace()
+        qo, qdo = o.substep_trace()
         vscale = np.maximum(1.0, np.abs(qdo[0]).max(axis=1, keepdims=True))
-        worst_v = max(worst_v, float(np.max(np.abs(qdo[0] - qdg[0]) / vscale))); worst_q = max(worst_q, _maxerr(qo[0], qg[0]))
+        for env in (g, d):
+            qg, qdg = env.substep_trace()
+            worst_v = max(worst_v, float(np.max(np.abs(qdo[0] - qdg[0]) / vscale))); worst_q = max(worst_q, _maxerr(qo[0], qg[0]))
     qa = np.random.RandomState(2).uniform(-0.5, 0.5, (8, 28)); qa[:, 3:7] /= np.linalg.norm(qa[:, 3:7], axis=1, keepdims=True)
     qd = np.random.RandomState(3).randn(8, 27); tau = np.random.RandomState(4).randn(8, 21) * 20
     ref = make_oracle(kind, 1)
-    qo2, qdo2 = ref.aba_substep(qa, qd, tau); qg2, qdg2 = g.aba_substep(qa, qd, tau)
+    qo2, qdo2 = ref.aba_substep(qa, qd, tau); qg2, qdg2 = d.aba_substep(qa, qd, tau)
     o.close(); g.close(); d.close(); ref.close()
     assert worst_v < 1e-3 and worst_q < 5e-6, (worst_v, worst_q)
     assert np.max(np.abs(qdo2 - qdg2) / np.maximum(1.0, np.abs(qdo2))) < 5e-4 and _maxerr(qo2, qg2) < 1e-5

@@ -10,7 +10,7 @@ mkdir -p variants
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared -I include"
 SRC=steppingstone_b200/csrc
 nvcc $FLAGS -I $SRC                    -o variants/libss_default.so $SRC/ss_kernels.cu &
-nvcc $FLAGS -I $SRC -DSS_SPARSE_LDL=1  -o variants/libss_sparse_ldl.so $SRC/ss_kernels.cu &
+nvcc $FLAGS -I $SRC -DSS_SPARSE_LDL=0  -o variants/libss_dense_ldl.so $SRC/ss_kernels.cu &
 nvcc $FLAGS -I $SRC -DSS_FAST_DIV=0    -o variants/libss_ieee_div.so $SRC/ss_kernels.cu &
 for extra in "$@"; do   # e.g. tools/build_variants.sh "-DSS_WPB=16"  ->  variants/libss__DSS_WPB_16.so
   nvcc $FLAGS -I $SRC $extra -o "variants/libss_$(echo "$extra" | tr -c 'A-Za-z0-9\n' '_').so" $SRC/ss_kernels.cu &

@@ -19,7 +19,8 @@ walker" that dwells on each stone (stone advances, step bonus, plank ring buffer
 truncation); (C) the same with stop_frames=5 and no time limit, to reach the last stone (target bonus, index clamp);
 (D) ghost tapes that call create_temp_states_1/_2/create_temp_states after every stone advance; (E) a Mike ghost tape that
 calls update_sample_prob with a fresh sparse 11^5 table after stone advances (immediate re-sample + later draws);
-(F) the reference's shipped policies walking the stones in the oracle's simulation (closed loop), replayed through the
+(G) the same with a 23-step time limit, so that episodes END on stone-advance steps: reset() leaves update_terrain
+set and the following update_sample_prob acts on the freshly reset env; (F) the reference's shipped policies walking the stones in the oracle's simulation (closed loop), replayed through the
 reference env: stone advances by physical foot contact, step bonuses and progress rewards on realistic gaits.
 """
 import os
@@ -123,7 +124,7 @@ class RefWorker:
 
 
 def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=None, curriculum=None, oracle_params=None,
-           temp_states=False, sample_prob_every=0):
+           temp_states=False, sample_prob_every=0, sample_prob_at_done=False):
     """tape_fn(t, worker, sim) -> (q, qd, contact) for step t.  temp_states: after every step that advanced a stone
     call the reference's create_temp_states_1 / _2 / create_temp_states (value-guided sampling probes) and record them."""
     fk = make_oracle(kind, seed)
@@ -143,10 +144,12 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
         EPR.append(info["episode"]["r"] if "episode" in info else 0.0)
         EPL.append(info["episode"]["l"] if "episode" in info else 0)
         NXT.append(nxt); CNT.append(cnt); POT.append(pot)
-        if sample_prob_every and not d and w.env.update_terrain and (nxt % sample_prob_every) != 0:
+        if sample_prob_every and (not d or sample_prob_at_done) and w.env.update_terrain and (d or (nxt % sample_prob_every) != 0):
             # update_sample_prob (mike.py:827-830 through envs_utils.py:568-571) right after a step that advanced a stone
             # (the only moment the reference env takes the table): new sampling table + immediate re-sample of the
             # next-next stone.  Skipped on every third stone so that draws from a table set earlier are covered too.
+            # sample_prob_at_done: also after an episode that ENDED on an advance step -- reset() does not clear
+            # update_terrain, so the freshly reset env takes the table and re-samples its stone 2 (tape G).
             table = sp_rng.rand(11, 11, 11, 11, 11) * (sp_rng.rand(11, 11, 11, 11, 11) < 0.02)
             table[5, 5, 0, 5, 5] += 1e-3
             table = table.astype(np.float32).astype(np.float64)          # stored as float32 in the fixture: keep it exact
@@ -179,8 +182,8 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
                                      e.fake_y_tilt_samples]), **ts_data)
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
-    print("%-28s T=%d episodes=%d max next_step=%d reward[min,max]=[%.2f, %.2f]" % (
-        name, T, int(np.sum(DONE)), int(np.max(NXT)), np.min(REW), np.max(REW)))
+    print("%-28s T=%d episodes=%d max next_step=%d reward[min,max]=[%.2f, %.2f] sample_prob calls %d (%d right after a done step)" % (
+        name, T, int(np.sum(DONE)), int(np.max(NXT)), np.min(REW), np.max(REW), len(sp_step), sum(bool(DONE[t]) for t in sp_step)))
 
 
 def simulated_tape(kind, seed, actions, T, curriculum=None):
@@ -255,6 +258,15 @@ def ghost_tape(kind, seed, rng, dwell):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only in (None, "mike_ghost_sampleprob_at_done"):
+        T = 200
+        rng = np.random.RandomState(67)
+        acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)
+        record("mike_ghost_sampleprob_at_done", 1, 15, acts, ghost_tape(1, 15, rng, 6), T, time_limit=23,
+               env_params={"stop_frames": 5}, curriculum=5, sample_prob_every=3, sample_prob_at_done=True)
+        if only:
+            return
     for kind, nm in ((0, "w3d"), (1, "mike")):
         for seed in (8, 9):
             T = 220

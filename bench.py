@@ -61,6 +61,54 @@ WORKLOADS = {
     "mike": dict(env_id="mocca_envs:MikeStepperEnv-v0", kind=1, terrain_mode=None, curriculum=5,
                  name="MikeStepperEnv-v0 use_curriculum (level 5: yaw +-20, pitch +-50)"),
 }
+# The reference's shipped policies (weights read as data: tests/golden/policies/*.npz, tools/read_legacy_checkpoint.py)
+# as the action source: the characters WALK the stones (~6 contact points per env and substep) instead of flailing under
+# random actions -- the state mix a training run spends its time in once the policy works.
+WALK_POLICY = {"w3d-flat": "w3d_base", "w3d": "w3d_latest", "mike": "mike_latest"}
+for _k in list(WALK_POLICY):
+    WORKLOADS[_k + "-walk"] = dict(WORKLOADS[_k], policy=WALK_POLICY[_k],
+                                   name=WORKLOADS[_k]["name"] + ", actions from the reference's shipped policy " + WALK_POLICY[_k] + " (walking states)")
+WALK_WARMUP = 200      # policy steps before the timed region of a walking workload: the gait is established, stones are being reached
+
+
+def load_actor(tag, dev):
+    """common/controller.py:193-201 SoftsignActor.forward, deterministic (action = mean), as playground/enjoy.py runs it."""
+    import torch
+    f = torch.nn.functional
+    z = np.load(os.path.join(ROOT, "tests", "golden", "policies", tag + ".npz"))
+    P = {k: torch.tensor(z[k], device=dev) for k in z.files if k.endswith(("_w", "_b"))}
+
+    @torch.no_grad()
+    def actor(x):
+        x = f.softsign(f.linear(x, P["fc1_w"], P["fc1_b"])); x = f.softsign(f.linear(x, P["fc2_w"], P["fc2_b"]))
+        x = f.softsign(f.linear(x, P["fc3_w"], P["fc3_b"]))
+        x = torch.relu(f.linear(x, P["fc4_w"], P["fc4_b"])); x = torch.relu(f.linear(x, P["fc5_w"], P["fc5_b"]))
+        return torch.tanh(f.linear(x, P["out_w"], P["out_b"])).contiguous()
+    return actor
+
+
+def timed_steps(env, next_action, K, flush, barrier, obs0):
+    """K control steps, each bracketed by its own CUDA-event pair on the launching stream; the L2 flush and the action
+    source (ring lookup or policy forward) sit OUTSIDE the pair.  Returns per-step ms, wall seconds."""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    obs = obs0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xff)                      # L2 flush between timed steps (outside the event pair)
+        a = next_action(i, obs)
+        ev[i][0].record()
+        obs, _, _, _ = env.step(a)
+        ev[i][1].record()
+    barrier()
+    return np.array([a_.elapsed_time(b_) for a_, b_ in ev]), time.perf_counter() - t0, obs
+
+
+def mean_contacts(env):
+    """contact points per env in the last substep (the warm-start list), from the device state."""
+    w = env.get_state()["warm"][:, :8]
+    return float((w >= 0).sum(axis=1).mean())
 
 
 def measured_peaks():
@@ -204,26 +252,82 @@ def cpu_port_rate(wl, n_envs, steps, warmup, threads=0, seed=8):
     return n_envs * steps / dt, dt
 
 
+def _real_reference_worker(env_id, seed, steps, warmup, q):
+    """One reference env (the unmodified mocca_envs class on PyBullet) stepped in its own process, as a SubprocVecEnv
+    worker does (common/envs_utils.py:623-675): random actions of the workload's distribution, auto-reset on done."""
+    import gym
+    env = gym.make(env_id); env.seed(seed); env.reset()
+    rng = np.random.RandomState(seed)
+    t0 = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        _, _, d, _ = env.step(np.clip(rng.randn(21) * 0.22, -1, 1).astype(np.float32))
+        if d:
+            env.reset()
+    q.put(time.perf_counter() - t0)
+
+
+def real_reference_rate(wl, steps, warmup):
+    """The REAL reference (PyBullet) on all host cores, if it can run here: needs `pybullet`, `gym` (< 0.22) and the
+    reference's `mocca_envs` package (baseline/_ref: `pip install --no-deps --target baseline/_ref` of the reference's
+    .environments/, done by __graft_entry__.build() where /root/reference exists).  Returns (rate, cores, None) or
+    (None, None, reason).  Probed on the GPU box in round 2: profiles/r02a_probe_reference_deps.log -- neither module
+    exists there, no wheel in /opt/wheelhouse, no network."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    missing = []
+    for mod in ("pybullet", "gym", "mocca_envs"):
+        try:
+            __import__(mod)
+        except Exception as exc:                    # ModuleNotFoundError, or mocca_envs failing on ITS imports
+            missing.append("%s: %s" % (mod, repr(exc)[:80]))
+    if missing:
+        return None, None, "; ".join(missing)
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    q = mp.Queue()
+    procs = [mp.Process(target=_real_reference_worker, args=(wl["env_id"], 8 + i, steps, warmup, q)) for i in range(cores)]
+    for p_ in procs:
+        p_.start()
+    times = [q.get() for _ in procs]
+    for p_ in procs:
+        p_.join()
+    return cores * steps / max(times), cores, None
+
+
 def run_reference(args, wl):
-    """--impl reference: the reference's CPU implementation of the path.  PyBullet (where the reference's
-    physics lives) is absent from the reference tree and from this image, so this arm times the oracle port
-    (kind "port") on all host threads, on a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  First choice: the real
+    reference (real_reference_rate).  PyBullet, where the reference's physics lives, is absent from the reference tree,
+    from this image and from the GPU box, so in practice this arm times the oracle port (kind "port") on all host threads
+    -- and says so, with the reason, on its line.  Same workload and batch size as the GPU arm (`--ref-envs` = --envs)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_envs = args.ref_envs
-    rate, dt = cpu_port_rate(wl, n_envs, args.steps, args.warmup)
-    sample = "%d envs x %d steps (of the %d-env workload), %d OpenMP threads" % (n_envs, args.steps, args.envs, cores)
+    n_envs = args.ref_envs or args.envs
+    kind, probe = "port", None
+    rate, rcores, why = real_reference_rate(wl, args.steps, args.warmup) if "policy" not in wl else (None, None, "walking workloads use the port")
+    if rate is not None:
+        kind, cores, dt = "reference", rcores, args.steps * rcores / rate
+        sample = "%d reference envs (one process per core, gym.make + PyBullet) x %d steps each" % (rcores, args.steps)
+        n_envs = rcores
+    else:
+        probe = {"real_reference": "unavailable", "why": why, "gpu_box_probe": "profiles/r02a_probe_reference_deps.log"}
+        rate, dt = cpu_port_rate(wl, n_envs, args.steps, args.warmup)
+        sample = "%d envs x %d steps (the GPU arm steps %d envs per GPU), %d OpenMP threads" % (n_envs, args.steps, args.envs, cores)
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_step": n_envs, "actions": "clip(N(0,0.22),-1,1)"},
-        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if probe:
+        line["reference_probe"] = probe
     emit(line)
 
 
@@ -252,11 +356,17 @@ def run_b200(args, wl):
                             terrain_mode=wl["terrain_mode"])
     if wl["curriculum"] is not None:
         env.update_curriculum(wl["curriculum"])
-    env.reset()
+    obs = env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
     ring = 64
     acts = torch.clamp(torch.randn(ring, N, 21, device=dev, generator=gen) * 0.22, -1, 1).contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    actor = load_actor(wl["policy"], dev) if "policy" in wl else None
+    if actor is not None:
+        W = max(W, WALK_WARMUP)
+        next_action = lambda i, o: actor(o)
+    else:
+        next_action = lambda i, o: acts[(W + i) % ring]
 
     try:
         uuid = str(torch.cuda.get_device_properties(local).uuid)   # CUDA_VISIBLE_DEVICES may renumber the GPUs
@@ -265,23 +375,15 @@ def run_b200(args, wl):
     sampler = ClockSampler(local, uuid); sampler.start()
     sampler.mark()
     for i in range(W):
-        env.step(acts[i % ring])
+        obs, _, _, _ = env.step(actor(obs) if actor is not None else acts[i % ring])
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     l0 = env.launch_count
-    barrier()
     if sampler.source == "nvml":
         sampler.mark()                             # NVML: samples of the timed region only (the fallback keeps the warm-up's too)
-    t_wall0 = time.perf_counter()
-    for i in range(K):
-        flush.fill_(i & 0xff)                      # L2 flush between timed steps (outside the event pair)
-        ev[i][0].record()
-        _, _, done, _ = env.step(acts[(W + i) % ring])
-        ev[i][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
+    step_ms, t_wall, obs = timed_steps(env, next_action, K, flush, barrier, obs)
     launches = env.launch_count - l0
     clocks = sampler.stop()
+    contacts_main = mean_contacts(env)
     if world > 1:                                  # every rank samples its own GPU; rank 0 reports the slowest + all reasons
         names = ClockSampler.NAMES
         cmin = torch.tensor([clocks["sm_mhz"] if clocks["sm_mhz"] is not None else float("inf")], dtype=torch.float64, device=dev)
@@ -292,7 +394,6 @@ def run_b200(args, wl):
         clocks = dict(clocks, reasons=sorted(other + [n_ for n_, f_ in zip(names, flags.tolist()) if f_ > 0]),
                       sm_mhz_rank0=clocks["sm_mhz"], ranks=world)
         clocks["sm_mhz"] = None if cmin.item() == float("inf") else float(cmin.item())
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     t_dev = float(step_ms.sum()) * 1e-3
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
     if world > 1:
@@ -353,6 +454,32 @@ def run_b200(args, wl):
         abaL_ms.append(a.elapsed_time(b))
     abaL_s = float(np.mean(abaL_ms)) * 1e-3
 
+    # ---- the same kernel on WALKING states (the random-action mix is light): the reference's shipped policy
+    #      drives a second env of the same workload; only env.step sits inside the event pairs ----
+    walking = None
+    wk = args.workload + "-walk"
+    if actor is None and wk in WORKLOADS and not args.no_walking:
+        try:
+            wlw = WORKLOADS[wk]
+            env_w = BatchedStepperEnv(wlw["env_id"], 8, N, device=local, output="torch", first_env=rank * N, terrain_mode=wlw["terrain_mode"])
+            if wlw["curriculum"] is not None:
+                env_w.update_curriculum(wlw["curriculum"])
+            actor_w = load_actor(wlw["policy"], dev)
+            ob = env_w.reset()
+            for _ in range(WALK_WARMUP):
+                ob, _, _, _ = env_w.step(actor_w(ob))
+            Kw = max(16, min(K, 128))
+            ms_w, _, ob = timed_steps(env_w, lambda i, o: actor_w(o), Kw, flush, barrier, ob)
+            tw = torch.tensor([float(ms_w.sum()) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            walking = {"workload": wlw["name"], "value": world * N * Kw / float(tw.item()), "unit": "env-steps/s",
+                       "ms_per_step": float(tw.item()) / Kw * 1e3, "steps": Kw, "policy_warmup_steps": WALK_WARMUP,
+                       "contacts_per_env": mean_contacts(env_w)}
+            env_w.close()
+        except Exception as exc:
+            walking = {"error": repr(exc)[:200]}
+
     # ---- create_temp_states fill kernel (value-guided sampling probes): the one HBM-bound kernel of the path,
     #      240 B written per (env, grid cell); 48 envs x 161051 cells = 1.86 GB per launch (> L2, no flush needed) ----
     tsf = None
@@ -410,7 +537,7 @@ def run_b200(args, wl):
                        "actions": "clip(N(0,0.22),-1,1), 64-batch ring resident in HBM", "parallelism": "env-sharded x%d" % world,
                        "l2": "flushed between timed steps (256 MiB write outside the event pair)",
                        "timing": "sum of per-step CUDA-event durations, max over ranks",
-                       "wall_ms_per_step_incl_flush": t_wall / K * 1e3},
+                       "wall_ms_per_step_incl_flush": t_wall / K * 1e3, "contacts_per_env": contacts_main},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * H2D_PER_ENV,
                     "d2h_bytes_per_step": N * D2H_PER_ENV, "steps": Ke, "api": "BatchedStepperEnv.step (numpy mode) -> ss_step_host"},
             "gpu_launches": int(launches),
@@ -432,6 +559,8 @@ def run_b200(args, wl):
                 tsf.update(kernel="temp_prep_kernel + temp_fill_kernel", bound="hbm", peak=peak, unit="GB/s", frac=tsf["achieved"] / peak,
                            algorithmic_bytes_per_env_cell=240)
             line["roofline_temp_states"] = tsf
+        if walking is not None:
+            line["walking"] = walking
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)
@@ -448,8 +577,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=8192, help="envs per GPU")
     ap.add_argument("--workload", default="w3d-flat", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-envs", type=int, default=2048, help="envs per step of the CPU arm's bounded sample")
+    ap.add_argument("--ref-envs", type=int, default=0, help="envs per step of the CPU arm (0 = the GPU arm's --envs: same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-walking", action="store_true", help="skip the secondary measurement on walking states")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -31,7 +31,7 @@ extern "C" {
 #define SS_NWARM 16      /* warm-start cache: ids of the last substep's <= 8 contacts (-1 = none), then their normal impulses */
 #define SS_NSCAL 16      /* doubles per env in ss_state_view.scalars                              */
 #define SS_NINT 8        /* int32 per env in ss_state_view.ints                                   */
-#define SS_NEV 10        /* int32 per env and substep in the discrete-event trace (ss_substep_events)   */
+#define SS_NEV 18        /* int32 per env and substep in the discrete-event trace (ss_substep_events)   */
 #define SS_MT_WORDS 625  /* MT19937: 624 state words + position                                   */
 
 /* scalars[]: */
@@ -129,7 +129,13 @@ int ss_enable_substep_trace(ss_env* env, int32_t on);
 int ss_substep_trace(ss_env* env, double* q_host, double* qd_host);
 /* The DISCRETE decisions each of those substeps took: ev_host [4,N,SS_NEV] int32 = bit j set: hinge j got a lower-limit row
  * (btMultiBodyJointLimitConstraint: q - lo <= 0), same for the upper limit (bit 30 of that word: the max_coord_vel safety
- * clamp engaged in this substep), then the ids of the <= 8 contact points that entered the solver (-1 = none).  A limit row or a contact point exists or not, so fp32 rounding can flip such a decision
+ * clamp engaged in this substep), then the <= 8 contact points that entered the solver (-1 = none): contact id in the low
+ * 16 bits, above it the branch of the contact geometry that produced the point (bit 16 btPlaneSpace1's |n.z| > 0.7071
+ * friction basis, bit 17 capsule segment off the plank's footprint, bit 18 point inside the box, bits 19-20 its face axis).
+ * Words 10..17: per contact, bit `it` set iff its normal impulse was > 0 when solver iteration `it` refreshed the friction
+ * bounds.  Bullet skips a friction row while its normal impulse is zero (`if (totalImpulse > 0)` in
+ * btMultiBodyConstraintSolver::solveSingleIteration), so the row keeps whatever impulse it had: the iteration at which a
+ * normal lets go is a discrete event too, with a first-order effect on light links.  A limit row or a contact point exists or not, so fp32 rounding can flip such a decision
  * where the fp64 reference sits within rounding of the threshold; the parity tests compare trajectories conditional on
  * equal decisions and account for every flip.  Needs ss_enable_substep_trace. */
 int ss_substep_events(ss_env* env, int32_t* ev_host);

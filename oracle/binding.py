@@ -157,7 +157,7 @@ class Oracle:
         return q, qd
 
     def substep_events(self):
-        ev = np.zeros((4, self.n, 10), np.int32)
+        ev = np.zeros((4, self.n, 18), np.int32)
         assert self.lib.sso_substep_events(self.h, _ptr(ev)) == 0
         return ev
 

@@ -364,7 +364,10 @@ static void contact_jacobian(const ss_model* M, const kin_t* K, int body, const 
  * (collision_mode 2): one closest-point pair per geom pair of M->pair_a/b -> id SS_NGEOM*8 + pair.  The SS_MAX_CONTACTS
  * deepest candidates (ties by id) become contacts, ordered by id.
  * ---------------------------------------------------------------------------------------------- */
-typedef struct { int active, id, body, body_b; double depth, n[3], x[3], xb[3]; } cand_t;
+typedef struct { int active, id, body, body_b, code; double depth, n[3], x[3], xb[3]; } cand_t;
+/* cand_t.code: which branch of the contact geometry produced the point (parity probe, sso_substep_events): bit 1 the
+ * segment missed the plank's footprint (whole segment kept), bit 2 the point lies inside the box (face normal), bits 3-4 that
+ * face's axis.  Bit 0 is added by the row set-up: btPlaneSpace1's |n.z| > 0.7071 branch (the friction basis). */
 #define MAXCAND (SS_NGEOM * 8 + SS_MAX_PAIRS)
 
 static void plank_box(const ss_params* P, const double* pl, double* Rs, double* cb) {
@@ -394,7 +397,8 @@ static int capsule_box(const ss_params* P, const double* Rs, const double* cb, c
             if (tb < t1) t1 = tb;
         }
     }
-    if (empty || t0 > t1) { t0 = 0; t1 = 1; }
+    c->code = 0;
+    if (empty || t0 > t1) { t0 = 0; t1 = 1; c->code |= 2; }
     if (end == 1 && t1 - t0 < 1e-6) return 0;
     double tt = end ? t1 : t0, s[3], q[3], nl[3], dist;
     for (int i = 0; i < 3; i++) s[i] = a[i] + tt * (bb[i] - a[i]);
@@ -413,6 +417,7 @@ static int capsule_box(const ss_params* P, const double* Rs, const double* cb, c
         for (int i = 0; i < 3; i++) { double m = P->stone_half[i] - fabs(s[i]); if (m < best) { best = m; ax = i; } }
         nl[0] = nl[1] = nl[2] = 0; nl[ax] = s[ax] >= 0 ? 1.0 : -1.0;
         dist = -best;
+        c->code |= 4 | (ax << 3);
     }
     c->depth = dist - r;
     if (!(c->depth < breaking)) return 0;
@@ -634,8 +639,9 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
     /* the substep's discrete decisions (parity probe: sso_substep_events) */
     e->ev_cur[0] = e->ev_cur[1] = 0;
     for (int r = 0; r < nl; r++) for (int j = 0; j < NJ; j++) if (rows[r].J[6 + j] != 0) e->ev_cur[rows[r].J[6 + j] > 0 ? 0 : 1] |= 1 << j;
-    for (int c = 0; c < MAXC; c++) e->ev_cur[2 + c] = c < nc ? con[c].id : -1;
+    for (int c = 0; c < MAXC; c++) e->ev_cur[2 + c] = c < nc ? (con[c].id | ((con[c].code | (fabs(con[c].n[2]) > 0.7071067811865475244008443621048490 ? 1 : 0)) << 16)) : -1;
     if (clamped) e->ev_cur[1] |= 1 << 30;           /* the max_coord_vel safety clamp engaged (before the solve) */
+    for (int c = 0; c < MAXC; c++) e->ev_cur[10 + c] = 0;
     if (nr > 0) {
         double dv[ND]; memset(dv, 0, sizeof dv);
         for (int r = 0; r < nr; r++) if (rows[r].lam != 0) for (int k = 0; k < ND; k++) dv[k] += rows[r].W[k] * rows[r].lam;
@@ -646,6 +652,7 @@ static void substep(const ss_model* M, const ss_params* P, env_t* e, const doubl
                 row_t* r = &rows[ri];
                 if (r->normal >= 0) {
                     double tot = rows[r->normal].lam;
+                    if (tot > 0 && it < 31) e->ev_cur[10 + (r->normal - nl)] |= 1 << it;     /* solver history (parity probe) */
                     if (!(tot > 0)) continue;
                     r->lo = -r->mu * tot; r->hi = r->mu * tot;
                 }

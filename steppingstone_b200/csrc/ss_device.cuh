@@ -601,12 +601,12 @@ __device__ __forceinline__ void integrate_warp(const DevModel& M, float* quat, f
 // normal impulse of each contact is looked up in the previous substep's list (`warm`: lanes 0..7 ids, 8..15 impulses).
 // Passes whose candidates are all out of reach (bounding test) are skipped.  Returns the number of contacts.
 // ---------------------------------------------------------------------------------------------
-struct Cand { bool active; float depth; int id; float n[3], x[3], xb[3]; int ba, bb; };
+struct Cand { bool active; float depth; int id; float n[3], x[3], xb[3]; int ba, bb, code; };    // code: geometry branch (parity probe, see ss_substep_events)
 
 __device__ __forceinline__ void con_write(float* c, const Cand& k) {
     c[0] = k.n[0]; c[1] = k.n[1]; c[2] = k.n[2]; c[3] = k.x[0]; c[4] = k.x[1]; c[5] = k.x[2];
     c[6] = k.depth; c[7] = (float)k.ba; c[8] = (float)k.id; c[9] = 0.f;
-    c[10] = k.xb[0]; c[11] = k.xb[1]; c[12] = k.xb[2]; c[13] = (float)k.bb;
+    c[10] = k.xb[0]; c[11] = k.xb[1]; c[12] = k.xb[2]; c[13] = (float)k.bb; c[14] = (float)k.code;
 }
 
 __device__ __noinline__ int pool_merge_slow(WarpSmem* Wp, int npool, bool active, float depth, int id, const float* rec, int lane) {
@@ -662,7 +662,7 @@ __device__ __forceinline__ void pool_add(WarpSmem& W, int& npool, const Cand& k,
         return;
     }
     float rec[16];
-    con_write(rec, k); rec[14] = rec[15] = 0.f;
+    con_write(rec, k); rec[15] = 0.f;
     npool = pool_merge_slow(&W, npool, k.active, k.depth, k.id, rec, lane);
 }
 
@@ -686,7 +686,7 @@ __device__ __forceinline__ void stone_candidate(const DevModel& M, const float* 
             t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
         }
     }
-    if (empty || t0 > t1) { t0 = 0.f; t1 = 1.f; }
+    if (empty || t0 > t1) { t0 = 0.f; t1 = 1.f; k.code |= 2; }
     if (endp == 1 && t1 - t0 < 1e-6f) return;
     float tt = endp ? t1 : t0, s[3], q[3], nl[3], dist;
     bool inside = true;
@@ -710,6 +710,7 @@ __device__ __forceinline__ void stone_candidate(const DevModel& M, const float* 
         float sg = (ax == 0 ? s[0] : (ax == 1 ? s[1] : s[2])) >= 0.f ? 1.f : -1.f;
         if (ax == 0) nl[0] = sg; else if (ax == 1) nl[1] = sg; else nl[2] = sg;
         dist = -best;
+        k.code |= 4 | (ax << 3);
     }
     const float r = g[6];
     k.depth = dist - r;
@@ -764,7 +765,7 @@ __device__ __forceinline__ int collide_warp(const DevModel& M, WarpSmem& W, cons
     int npool = 0;
     // ---- stones ----
     for (int base = 0; base < M.n_scand; base += 32) {
-        Cand k; k.active = false; k.depth = 0.f; k.id = 0; k.ba = 0; k.bb = -1;
+        Cand k; k.active = false; k.depth = 0.f; k.id = 0; k.ba = 0; k.bb = -1; k.code = 0;
         const int ci = base + lane;
         bool near = false;
         int g = 0, slot = 0, endp = 0;
@@ -795,7 +796,7 @@ __device__ __forceinline__ int collide_warp(const DevModel& M, WarpSmem& W, cons
     // ---- the robot against itself ----
     if (M.collision_mode >= 2) {
         for (int base = 0; base < M.n_pair; base += 32) {
-            Cand k; k.active = false; k.depth = 0.f; k.id = 0; k.ba = 0; k.bb = -1;
+            Cand k; k.active = false; k.depth = 0.f; k.id = 0; k.ba = 0; k.bb = -1; k.code = 0;
             const int pi = base + lane;
             bool near = false;
             int ga = 0, gb = 0;
@@ -852,7 +853,7 @@ __device__ __forceinline__ int collide_warp(const DevModel& M, WarpSmem& W, cons
             rec[9] = lam0;
             float* c = W.con[rank];
 #pragma unroll
-            for (int i = 0; i < 14; i++) c[i] = rec[i];
+            for (int i = 0; i < 15; i++) c[i] = rec[i];
             const int ba = (int)rec[7], bb = (int)rec[13];
             f0 = ba == M.foot_body[0] || bb == M.foot_body[0];
             f1 = ba == M.foot_body[1] || bb == M.foot_body[1];
@@ -871,7 +872,8 @@ __device__ __forceinline__ int collide_warp(const DevModel& M, WarpSmem& W, cons
 // ---------------------------------------------------------------------------------------------
 template <bool DIAG>
 __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, float* quat, float& q_dof, float& v_dof,
-                                            float tau_dof, float* dpos, float& warm, int lane, float* dbg, bool* clamp_hit = nullptr) {
+                                            float tau_dof, float* dpos, float& warm, int lane, float* dbg, bool* clamp_hit = nullptr,
+                                            unsigned* push_hist = nullptr) {
     const float hdt = M.dt;
     float acc = dynamics_warp<DIAG>(M, W, quat, q_dof, v_dof, tau_dof, lane, dbg);
     float vs = v_dof + hdt * acc;
@@ -1149,6 +1151,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
             // friction rows of a contact that does not push are no-ops (bounds pinned to the current impulse; Bullet skips
             // them too: `if (totalImpulse > 0)` in solveSingleIteration): skip the pair's four row steps, warp-uniformly
             const unsigned pushing = __ballot_sync(FULL, lam > 0.f) & ((1u << MAXC) - 1u);
+            if (DIAG && push_hist && it < 31) *push_hist |= ((pushing >> (lane & (MAXC - 1))) & 1u) << it;   // lane = contact (parity probe)
 #pragma unroll
             for (int k = 0; k < MAXC; k += 2)
                 if ((pushing >> k) & 3u) {

@@ -591,11 +591,16 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
                 const bool kept = lv != 0 && __popc(any & ((1u << lane) - 1u)) < MAXL;
                 ev_lo = __ballot_sync(FULL, kept && lv == 1) >> 6; ev_hi = __ballot_sync(FULL, kept && lv == 2) >> 6;
             }
-            bool clamp_hit = false;
-            cflags = substep_warp<DIAG>(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg, DIAG ? &clamp_hit : nullptr);
+            bool clamp_hit = false; unsigned push_hist = 0;
+            cflags = substep_warp<DIAG>(M, W, E.quat, E.q_dof, E.v_dof, tau, dpos, E.warm, lane, dbg, DIAG ? &clamp_hit : nullptr,
+                                        DIAG ? &push_hist : nullptr);
             if (DIAG && S.trace_ev && s < 4 && !ghost) {
                 int* ev = S.trace_ev + ((size_t)s * S.n + e) * SS_NEV;
-                if (lane < MAXC) ev[2 + lane] = (int)E.warm;           // contact ids of this substep (-1 = none)
+                if (lane < MAXC) {                 // contact ids of this substep (-1 = none) | geometry-branch code << 16
+                    const int id = (int)E.warm;
+                    ev[2 + lane] = id < 0 ? -1 : (id | (((int)W.con[lane][14] | (fabsf(W.con[lane][2]) > 0.70710678f ? 1 : 0)) << 16));
+                    ev[10 + lane] = id < 0 ? 0 : (int)push_hist;     // iterations in which this contact's normal impulse was > 0
+                }
                 if (lane == 0) { ev[0] = (int)ev_lo; ev[1] = (int)(ev_hi | (clamp_hit ? 1u << 30 : 0u)); }   // bit 30: max_coord_vel clamp engaged
             }
             if (DIAG && S.trace_q && s < 4 && !ghost) {
@@ -1102,6 +1107,7 @@ static int create_device_state(ss_env* E, const ss_model* model, const uint32_t*
         CK(cudaMemcpy(S.pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice));
     }
     CK(cudaStreamCreateWithFlags(&E->own, cudaStreamNonBlocking));
+    CK(cudaDeviceSynchronize());                     // the initial-state uploads above are pageable copies (see ss_set_state)
     return SS_OK;
 }
 
@@ -1261,9 +1267,15 @@ int ss_set_sample_cdf(ss_env* E, const double* cdf, int32_t n_cells, int32_t app
     // stream == NULL (host-buffer mode): the library's own stream, synchronised before returning.  The legacy default
     // stream would NOT do: ss_step_host works on cudaStreamNonBlocking streams, which do not wait for it, so the re-sample
     // (it writes terrain, planks and RNG state) could still be running when the next step starts.
+    // (a NULL stream is also what torch hands over while its current stream is the legacy default stream)
     cudaStream_t st = stream ? (cudaStream_t)stream : E->own;
+    if (!stream) CK(cudaDeviceSynchronize());       // whatever stream the caller's earlier work used (probes run on torch's)
     CK(cudaStreamSynchronize(st));
-    CK(cudaMemcpy(E->cdf, cdf, (size_t)n_cells * 8, cudaMemcpyHostToDevice));
+    // The table comes from pageable host memory.  A plain cudaMemcpy returns once the data is STAGED; the DMA itself is
+    // ordered in the legacy default stream only, which cudaStreamNonBlocking streams do not wait for -- the re-sample
+    // below (or the next ss_step_host) could read a half-written table.  Copy on the stream that uses it and wait.
+    CK(cudaMemcpyAsync(E->cdf, cdf, (size_t)n_cells * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
     if (apply_now) {
         resample_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S);
         E->launches++;
@@ -1286,6 +1298,7 @@ int ss_update_tables(ss_env* E, const ss_model* model, const ss_params* params, 
     CK(cudaStreamSynchronize(E->own));
     fill_model(E->hm, *model, *params);
     CK(cudaMemcpy(E->dm, &E->hm, sizeof(DevModel), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());                     // (pageable copy: see ss_set_state)
     return SS_OK;
 }
 
@@ -1373,6 +1386,9 @@ int ss_set_state(ss_env* E, const ss_state_view* v) {
     if (v->scalars) CK(cudaMemcpy(S.scal, v->scalars, N * SS_NSCAL * 8, cudaMemcpyHostToDevice));
     if (v->ints) CK(cudaMemcpy(S.ints, v->ints, N * SS_NINT * 4, cudaMemcpyHostToDevice));
     if (v->mt) CK(cudaMemcpy(S.mt, v->mt, N * 2 * SS_MT_WORDS * 4, cudaMemcpyHostToDevice));
+    // copies from pageable memory return once staged; their DMAs are ordered in the legacy default stream only, which the
+    // library's cudaStreamNonBlocking streams (ss_step_host) do not wait for: make "synchronous" true for every stream
+    CK(cudaDeviceSynchronize());
     return SS_OK;
 }
 
@@ -1388,6 +1404,7 @@ int ss_enable_substep_trace(ss_env* E, int32_t on) {
     } else if (!on && S.trace_q) {
         cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.trace_ev); S.trace_q = S.trace_qd = nullptr; S.trace_ev = nullptr;
     }
+    CK(cudaDeviceSynchronize());                     // the memsets above run in the legacy stream (see ss_set_state)
     return SS_OK;
 }
 
@@ -1419,6 +1436,7 @@ int ss_enable_debug(ss_env* E, int32_t on) {
     CK(cudaDeviceSynchronize());
     if (on && !E->S.dbg) { CK(cudaMalloc(&E->S.dbg, (size_t)E->n * DBG_FLOATS * 4)); CK(cudaMemset(E->S.dbg, 0, (size_t)E->n * DBG_FLOATS * 4)); }
     else if (!on && E->S.dbg) { cudaFree(E->S.dbg); E->S.dbg = nullptr; }
+    CK(cudaDeviceSynchronize());
     return SS_OK;
 }
 int ss_debug_read(ss_env* E, float* out_host) {
@@ -1451,7 +1469,7 @@ int ss_error_flags(ss_env* E, int32_t* flags, int32_t clear) {
     CK(cudaSetDevice(E->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(flags, E->S.err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (clear) CK(cudaMemset(E->S.err, 0, sizeof(int)));
+    if (clear) { CK(cudaMemset(E->S.err, 0, sizeof(int))); CK(cudaDeviceSynchronize()); }
     return SS_OK;
 }
 

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libss_b200.so")
 INCLUDE = os.path.join(REPO_DIR, "include")
 
 NQ, ND, NJ, OBS, NWARM, NSCAL, NINT, MTW, GRID_CELLS = 28, 27, 21, 60, 16, 16, 8, 625, 11 ** 5
+NEV = 18         # int32 per env and substep in ss_substep_events
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -387,8 +387,8 @@ class BatchedStepperEnv:
         return q, qd
 
     def substep_events(self):
-        """[4, N, 10] int32: lower / upper limit-row hinge masks and the <= 8 contact ids of each substep of the last step."""
-        ev = np.zeros((4, self.num_envs, 10), np.int32)
+        """[4, N, 18] int32: the discrete decisions of each substep of the last step (include/ss_env.h ss_substep_events)."""
+        ev = np.zeros((4, self.num_envs, native.NEV), np.int32)
         native.check(self._lib.ss_substep_events(self._h, ev.ctypes.data), "ss_substep_events")
         return ev
 

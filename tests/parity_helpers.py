@@ -3,12 +3,14 @@ B200) and by the CPU suite on the SIMT emulation of the same kernels (tests/test
 
 1. ``chain_check`` -- STRICT parity of chained substeps.  A physics substep takes discrete decisions: a joint-limit row
    exists iff ``q - lo <= 0`` (btMultiBodyJointLimitConstraint), a contact point enters the solver or not.  fp32 device
+   Which branch of the contact geometry produced a point, and the solver iteration at which a contact's normal impulse
+   drops to zero (Bullet then skips its friction rows, which keep their impulse), are decisions of the same kind.  fp32 device
    arithmetic and the fp64 oracle can decide differently where the state sits within rounding of such a threshold; from
    that substep on the two trajectories are different problems.  Both sides therefore record their decisions per substep
    (``ss_substep_events`` / ``sso_substep_events``) and the check is:
      * every env, at every substep up to which ALL decisions agree, is within the fp32 tolerance -- no quota;
      * every disagreement is accounted for: a limit-row flip must sit at a hinge within rounding of that limit in the
-       oracle's own state, contact flips are listed and bounded.
+       oracle's own state, contact / solver-history flips are counted and bounded.
    Envs whose velocity clamp (``max_coord_vel``, Bullet's 100 rad/s safety net) engaged in a substep -- both sides record
    that too, bit 30 of the event word -- are outside the regime the tolerance is stated for and are excluded from that
    substep on by that explicit criterion (and counted).
@@ -24,7 +26,7 @@ TOL_Q = np.array([5e-6, 2e-5, 8e-5, 2e-4])
 
 
 def chain_check(o, trace_o, trace_g, ev_o, ev_g, q_start, label="", max_flip_frac=0.15, max_contact_flip_frac=0.08):
-    """trace_* = (q [S,n,28], qd [S,n,27]); ev_* [S,n,10]; q_start [n,28] the common start state.
+    """trace_* = (q [S,n,28], qd [S,n,27]); ev_* [S,n,18]; q_start [n,28] the common start state.
     Returns ``strict`` [n]: envs whose decisions agree over the whole chain and whose clamp never engaged (for those the
     caller may compare observations / rewards too)."""
     qo, qdo = trace_o; qg, qdg = trace_g

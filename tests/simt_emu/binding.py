@@ -89,7 +89,7 @@ class EmuEnv:
         return q, qd
 
     def substep_events(self):
-        ev = np.zeros((4, self.n, 10), np.int32)
+        ev = np.zeros((4, self.n, native.NEV), np.int32)
         self._ck(self.lib.ss_substep_events(self.h, ev.ctypes.data), "ss_substep_events")
         return ev
 

@@ -105,6 +105,76 @@ def timed_steps(env, next_action, K, flush, barrier, obs0):
     return np.array([a_.elapsed_time(b_) for a_, b_ in ev]), time.perf_counter() - t0, obs
 
 
+def exchange_block(env, dev, world, rank, N, T, acts):
+    """BASELINE configs[3]: the rollout -> PPO-update boundary at `world` GPUs (playground/train.py:508-518).  Every rank
+    fills a device-resident [T+1, N, .] RolloutStorage by stepping its env shard, runs the GAE scan, then the exchange is
+    timed both ways: (a) the north star's plan -- NCCL all-gather of the rollout tensors (sharding.gather_rollout: every
+    rank ends up with the global [T+1, world*N, .] batch); (b) the data-parallel alternative -- shards stay local, global
+    advantage statistics + one flat gradient all-reduce per minibatch (sharding.global_advantage_stats /
+    allreduce_gradients).  Device-timed with CUDA events after a warm-up call, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from steppingstone_b200 import sharding
+    from steppingstone_b200.storage import RolloutStorage
+    free, _ = torch.cuda.mem_get_info(dev)
+    per_rank = (T + 1) * N * (60 + 21 + 7) * 4
+    need = per_rank * (2 * world + 1)                 # own shard + gathered copy + the largest field's staging buffer
+    asked = T
+    while need > 0.8 * free and T > 64:
+        T //= 2
+        per_rank = (T + 1) * N * (60 + 21 + 7) * 4; need = per_rank * (2 * world + 1)
+    ro = RolloutStorage(T, N, (60,), 21, 1, device=dev)
+    ro.observations[0].copy_(env.reset())
+    z1 = torch.zeros(N, 1, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(100 + rank)
+    torch.cuda.synchronize(dev); t0 = time.perf_counter()
+    for t in range(T):
+        a = acts[t % acts.shape[0]]
+        obs, rew, done, info = env.step(a)
+        ro.insert(obs, z1, a, z1, z1, rew.unsqueeze(1), (1.0 - done.float()).unsqueeze(1), (1.0 - info.bad_transition.float()).unsqueeze(1))
+    ro.value_preds.copy_(torch.randn(ro.value_preds.shape, device=dev, generator=gen))
+    torch.cuda.synchronize(dev); fill_s = time.perf_counter() - t0
+
+    def timed(fn, reps=1):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize(dev)
+        a_.record()
+        for _ in range(reps):
+            out = fn()
+        b_.record(); torch.cuda.synchronize(dev)
+        tt = torch.tensor([a_.elapsed_time(b_) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), out
+
+    gae_ms, _ = timed(lambda: ro.compute_returns(z1, True, 0.99, 0.95))
+    # (a) all-gather of the rollout (small warm-up first: communicator + allocator)
+    sharding.gather_rollout(ro, fields=("rewards",))
+    ms_g, g = timed(lambda: sharding.gather_rollout(ro))
+    out_bytes = sum(v.numel() * v.element_size() for v in g.values())
+    ok = tuple(g["observations"].shape) == (T + 1, world * N, 60) and bool(torch.equal(g["rewards"][:, rank * N:(rank + 1) * N], ro.rewards))
+    chk = g["rewards"].double().sum(); ref = chk.clone(); dist.broadcast(ref, 0)
+    ok = ok and bool(torch.equal(chk, ref))
+    del g
+    torch.cuda.empty_cache()
+    # (b) data-parallel alternative: advantage statistics + gradient all-reduce of the reference's actor + critic (~0.5 M parameters)
+    adv = ro.returns[:-1] - ro.value_preds[:-1]
+    sharding.global_advantage_stats(adv)
+    ms_adv, _ = timed(lambda: sharding.global_advantage_stats(adv), reps=5)
+    n_param = (60 * 256 + 256 + 4 * (256 * 256 + 256) + 256 * 21 + 21) + (60 * 256 + 256 + 3 * (256 * 256 + 256) + 256 + 1) + 21
+    params = [torch.nn.Parameter(torch.zeros(n_param, device=dev))]
+    params[0].grad = torch.randn(n_param, device=dev, generator=gen)
+    sharding.allreduce_gradients(params)
+    ms_gr, _ = timed(lambda: sharding.allreduce_gradients(params), reps=20)
+    n_mb = 10 * max(1, N * T // 32768)               # train.py:59-87: 10 epochs, minibatches of ~32k samples per rank
+    return {"rollout_T": T, "rollout_T_asked": asked, "envs_per_rank": N, "ranks": world, "shard_bytes_per_rank": per_rank,
+            "fill_s": fill_s, "fill_env_steps_per_s": world * N * T / fill_s, "gae_ms": gae_ms, "verified": ok,
+            "gather": {"collective": "ncclAllGather (all_gather_into_tensor per field, 9 fields) + one strided copy per field",
+                       "bytes_received_per_rank": out_bytes, "ms": ms_g, "GBps_into_each_rank": out_bytes / ms_g / 1e6,
+                       "nvlink5_per_direction_GBps": 900.0, "frac_of_nvlink": out_bytes * (world - 1) / world / ms_g / 1e6 / 900.0},
+            "data_parallel": {"collective": "ncclAllReduce", "advantage_stats_ms": ms_adv, "grad_allreduce_ms": ms_gr,
+                              "grad_bytes": n_param * 4, "allreduces_per_update": n_mb, "per_update_ms": ms_adv + n_mb * ms_gr}}
+
+
 def mean_contacts(env):
     """contact points per env in the last substep (the warm-start list), from the device state."""
     w = env.get_state()["warm"][:, :8]
@@ -412,11 +482,15 @@ def run_b200(args, wl):
     for i in range(3):
         env_h.step(acts_h[i % ring])
     barrier()
+    host4 = np.zeros(4); out4 = np.zeros(4)
     t0 = time.perf_counter()
     for i in range(Ke):
         obs_h, rew_h, done_h, infos_h = env_h.step(acts_h[(3 + i) % ring])
+        env_h._lib.ss_host_timing(env_h._h, out4.ctypes.data); host4 += out4
     barrier()
     t_e2e = time.perf_counter() - t0
+    host_us = dict(zip(("action_check_copy", "enqueue", "wait_device", "unpack"), (host4 / Ke * 1e6).round(1).tolist()))
+    host_us["python"] = round((t_e2e - host4.sum()) / Ke * 1e6, 1)
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -512,6 +586,13 @@ def run_b200(args, wl):
     except Exception as exc:                                  # never let the side measurement break the bench line
         tsf = {"error": repr(exc)[:200]}
 
+    exchange = None
+    if world > 1 and args.rollout > 0:
+        try:
+            exchange = exchange_block(env, dev, world, rank, N, args.rollout, acts)
+        except Exception as exc:
+            exchange = {"error": repr(exc)[:300]}
+
     peak, peak_src = measured_peaks()
     kern_s = t_dev / K
     achieved = ALG_BYTES_PER_ENV_STEP * N / kern_s / 1e9
@@ -539,7 +620,8 @@ def run_b200(args, wl):
                        "timing": "sum of per-step CUDA-event durations, max over ranks",
                        "wall_ms_per_step_incl_flush": t_wall / K * 1e3, "contacts_per_env": contacts_main},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * H2D_PER_ENV,
-                    "d2h_bytes_per_step": N * D2H_PER_ENV, "steps": Ke, "api": "BatchedStepperEnv.step (numpy mode) -> ss_step_host"},
+                    "d2h_bytes_per_step": N * D2H_PER_ENV, "steps": Ke, "api": "BatchedStepperEnv.step (numpy mode) -> ss_step_host",
+                    "host_us_per_step": host_us, "frac_of_device_rate": e2e_value / value},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "env_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -561,6 +643,8 @@ def run_b200(args, wl):
             line["roofline_temp_states"] = tsf
         if walking is not None:
             line["walking"] = walking
+        if exchange is not None:
+            line["exchange"] = exchange
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)
@@ -580,6 +664,8 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=0, help="envs per step of the CPU arm (0 = the GPU arm's --envs: same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-walking", action="store_true", help="skip the secondary measurement on walking states")
+    ap.add_argument("--rollout", type=int, default=2048,
+                    help="N > 1 only: length T of the rollout whose exchange step (configs[3]) is timed after the step metric; 0 = skip")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

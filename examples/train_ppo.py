@@ -25,15 +25,15 @@ import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from steppingstone_b200 import make_vec_envs, sharding            # noqa: E402
-from steppingstone_b200.collector import EpisodeStats, collect_rollout   # noqa: E402
+from steppingstone_b200.collector import EpisodeStats, GraphedRollout, collect_rollout   # noqa: E402
 from steppingstone_b200.storage import RolloutStorage             # noqa: E402
 
 
-def mlp(sizes, act, gain):
+def mlp(sizes, act, gain, out_gain=1.0):
     layers = []
     for i in range(len(sizes) - 1):
         lin = nn.Linear(sizes[i], sizes[i + 1])
-        nn.init.orthogonal_(lin.weight, gain=gain if i < len(sizes) - 2 else 1.0)
+        nn.init.orthogonal_(lin.weight, gain=gain if i < len(sizes) - 2 else out_gain)
         nn.init.zeros_(lin.bias)
         layers += [lin] + ([act()] if i < len(sizes) - 2 else [])
     return nn.Sequential(*layers)
@@ -68,12 +68,15 @@ class ActorCritic(nn.Module):
     """Policy.act / get_value / evaluate_actions (common/controller.py:106-150).  ``arch="reference"``: the shipped
     policies' SoftsignActor; ``"small"``: a 3-hidden-layer ReLU actor (faster, the default of the earlier logs)."""
 
-    def __init__(self, obs_dim, act_dim, h=256, arch="small", logstd=-1.5):
+    def __init__(self, obs_dim, act_dim, h=256, arch="small", logstd=-1.5, out_gain=1.0):
         super().__init__()
         if arch == "reference":
             self.actor = SoftsignActor(obs_dim, act_dim, h)
+            if out_gain != 1.0:
+                with torch.no_grad():
+                    self.actor.out.weight.mul_(out_gain); self.actor.out.bias.zero_()
         else:
-            self.actor = mlp([obs_dim, h, h, h, act_dim], nn.ReLU, nn.init.calculate_gain("relu"))
+            self.actor = mlp([obs_dim, h, h, h, act_dim], nn.ReLU, nn.init.calculate_gain("relu"), out_gain)
         self.critic = mlp([obs_dim, h, h, h, h, 1], nn.ReLU, nn.init.calculate_gain("relu"))
         self.logstd = nn.Parameter(torch.full((act_dim,), float(logstd)))  # DiagGaussian(noise=-1.5), controller.py:21
 
@@ -103,7 +106,7 @@ def ppo_update(ac, opt, rollouts, epochs, num_mini_batch, clip=0.2, max_grad_nor
         adv = (adv - mean) / (std + 1e-5)
     else:
         adv = (adv - adv.mean()) / (adv.std() + 1e-5)
-    vl = al = 0.0
+    vl = al = kl = 0.0
     for _ in range(epochs):
         for obs, states, actions, _, returns, masks, old_logp, adv_t in rollouts.feed_forward_generator(adv, num_mini_batch):
             values, logp, _, _ = ac.evaluate_actions(obs, states, masks, actions)
@@ -116,9 +119,12 @@ def ppo_update(ac, opt, rollouts, epochs, num_mini_batch, clip=0.2, max_grad_nor
                 sharding.allreduce_gradients(list(ac.parameters()))
             nn.utils.clip_grad_norm_(ac.parameters(), max_grad_norm)
             opt.step()
-            vl += value_loss.detach(); al += action_loss.detach()
+            vl += value_loss.detach(); al += action_loss.detach(); kl += (old_logp - logp).mean().detach()
     n = epochs * num_mini_batch
-    return float(vl) / n, float(al) / n
+    out = torch.stack([vl, al, kl]) / n
+    if distributed:                                   # every rank must see the same numbers (the adaptive lr depends on kl)
+        torch.distributed.all_reduce(out); out /= torch.distributed.get_world_size()
+    return tuple(out.tolist())
 
 
 def main():
@@ -144,7 +150,17 @@ def main():
     ap.add_argument("--critic-warmup", type=int, default=0,
                     help="iterations that train the critic only (use with --init-actor: the critic starts random)")
     ap.add_argument("--logstd", type=float, default=-1.5, help="initial log-std of the Gaussian policy (controller.py:21)")
+    # large-batch recipe (none of it is in the reference, whose 40 000-sample batches need none of it; all default off)
+    ap.add_argument("--reward-scale", type=float, default=1.0, help="rewards are multiplied by this before GAE (returns of ~500 -> O(5) for the critic)")
+    ap.add_argument("--kl-target", type=float, default=0.0, help="> 0: adapt the lr to keep the per-update KL near this (x1.5 / /1.5), instead of --lr-decay")
+    ap.add_argument("--out-gain", type=float, default=1.0, help="scale of the actor's last layer at initialisation (0.01: near-zero initial actions)")
+    ap.add_argument("--graph", action="store_true", help="collect each rollout by replaying ONE CUDA graph (collector.GraphedRollout)")
+    ap.add_argument("--tf32", action="store_true", help="TF32 matmuls in the policy / update (the env is unaffected)")
+    ap.add_argument("--gamma", type=float, default=0.99)
+    ap.add_argument("--log", default=None, help="rank 0 also appends its iteration lines to this file")
     args = ap.parse_args()
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
     # one process per GPU under torchrun: --envs is PER GPU (weak scaling, like bench.py); rank r owns the global env
     # indices [r * envs, (r + 1) * envs) with the reference's seed + index numbering (sharding.py)
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
@@ -163,7 +179,7 @@ def main():
         envs.update_curriculum(args.curriculum)
     if args.init_actor:
         args.arch = "reference"
-    ac = ActorCritic(60, 21, arch=args.arch, logstd=args.logstd).to(dev)
+    ac = ActorCritic(60, 21, arch=args.arch, logstd=args.logstd, out_gain=args.out_gain).to(dev)
     if args.init_actor:
         ac.actor.load_npz(args.init_actor)
     if distributed:
@@ -174,21 +190,41 @@ def main():
     num_mini_batch = max(1, args.envs * args.steps // args.mini_batch)
     t_start = time.time(); frames = 0
     curriculum = args.curriculum
+    stats = EpisodeStats(dev)
+    runner = GraphedRollout(envs, ac, rollouts, args.steps, stats, warmup=1) if args.graph else None
+    if runner is not None:
+        frames += args.envs * args.steps * world          # the capture's warm-up rollout (its data is discarded)
+    lr = args.lr
+    logf = open(args.log, "a") if (args.log and rank == 0) else None
+    reached = {}                                          # first time / frames at which the mean return passed a mark
     for it in range(args.iters):
-        lr = max(args.lr * args.lr_decay ** (frames / 40000.0), 3e-5)
+        if not args.kl_target:
+            lr = max(args.lr * args.lr_decay ** (frames / 40000.0), 3e-5)
         for g in opt.param_groups:
             g["lr"] = lr
-        stats = EpisodeStats(dev)
+        stats.sum.zero_(); stats.count.zero_(); stats.len_sum.zero_()
         t0 = time.time()
-        collect_rollout(envs, ac, rollouts, args.steps, stats)
+        if runner is not None:
+            runner.run()
+        else:
+            collect_rollout(envs, ac, rollouts, args.steps, stats)
+        stones = float((rollouts.rewards > 10.0).sum().item()) / (args.envs * args.steps) * 1000.0   # steps carrying a step bonus
+        rew_mean = float(rollouts.rewards.mean())
+        if args.reward_scale != 1.0:
+            rollouts.rewards.mul_(args.reward_scale)
         with torch.no_grad():
             next_value = ac.get_value(rollouts.observations[-1], None, None)
-        rollouts.compute_returns(next_value, True, 0.99, 0.95)
+        rollouts.compute_returns(next_value, True, args.gamma, 0.95)
         torch.cuda.synchronize(); t1 = time.time()
-        vl, al = ppo_update(ac, opt, rollouts, args.epochs, num_mini_batch, distributed=distributed,
-                            actor_frozen=it < args.critic_warmup)
+        vl, al, kl = ppo_update(ac, opt, rollouts, args.epochs, num_mini_batch, distributed=distributed,
+                                actor_frozen=it < args.critic_warmup)
         rollouts.after_update()
         torch.cuda.synchronize(); t2 = time.time()
+        if args.kl_target:                                # same kl on every rank (all-reduced) -> same lr everywhere
+            if kl > 2.0 * args.kl_target:
+                lr = max(lr / 1.5, 1e-5)
+            elif kl < 0.5 * args.kl_target:
+                lr = min(lr * 1.5, 1e-2)
         frames += args.envs * args.steps * world
         if distributed:                             # global finished-episode statistics drive the curriculum trigger
             mean_r, n_ep = sharding.reduce_episode_stats(stats.sum, stats.count)
@@ -196,13 +232,17 @@ def main():
         else:
             mean_r, n_ep = stats.mean()
             mean_l = float(stats.len_sum.item()) / max(n_ep, 1)
-        # stones reached per 1000 env-steps: a step carrying the step bonus (50 exp(-d/0.25), walker3d_envs.py:1001-1006)
-        stones = float((rollouts.rewards > 10.0).sum().item()) / (args.envs * args.steps) * 1000.0
+        for mark in (1000, 2000, 3000):
+            if n_ep > 0 and mean_r > mark and (mark, curriculum) not in reached:
+                reached[(mark, curriculum)] = (time.time() - t_start, frames)
         if rank == 0:
-            print("iter %4d frames %9d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  stones/1000steps %5.2f  value_loss %8.3f  "
-                  "curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy, %d GPU)  update %.2fs" % (
-                      it, frames, n_ep, mean_r, mean_l, float(rollouts.rewards.mean()), stones, vl, curriculum, lr,
-                      world * args.envs * args.steps / (t1 - t0), world, t2 - t1), flush=True)
+            line = ("iter %4d t %6.1fs frames %11d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  stones/1000steps %5.2f  "
+                    "value_loss %9.4f  kl %.4f  curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy, %d GPU)  update %.2fs" % (
+                        it, time.time() - t_start, frames, n_ep, mean_r, mean_l, rew_mean, stones, vl, kl, curriculum, lr,
+                        world * args.envs * args.steps / (t1 - t0), world, t2 - t1))
+            print(line, flush=True)
+            if logf:
+                logf.write(line + "\n"); logf.flush()
         if args.use_curriculum and n_ep > 0 and mean_r > 1000 and curriculum <= 4:      # train.py:503-506
             curriculum += 1
             envs.update_curriculum(curriculum)
@@ -213,6 +253,12 @@ def main():
             stop = bool(flag.item())
         if stop:
             break
+    if rank == 0:
+        summary = "summary: %d GPU(s), %d frames in %.1f s; " % (world, frames, time.time() - t_start) + "; ".join(
+            "mean return > %d at curriculum %d after %.1f s / %d frames" % (m, c, t, f) for (m, c), (t, f) in sorted(reached.items(), key=lambda kv: kv[1]))
+        print(summary, flush=True)
+        if logf:
+            logf.write(summary + "\n"); logf.close()
     envs.close()
     if distributed:
         torch.distributed.destroy_process_group()

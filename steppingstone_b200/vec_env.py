@@ -15,7 +15,12 @@ Two output modes:
 from __future__ import annotations
 
 import ctypes
+import json
+import os
+import sys
 import time
+from collections.abc import Sequence
+from itertools import repeat
 
 import numpy as np
 
@@ -46,6 +51,86 @@ class StepInfo:
 
     def __init__(self, done, bad_transition, episode_r, episode_l):
         self.done, self.bad_transition, self.episode_r, self.episode_l = done, bad_transition, episode_r, episode_l
+
+
+class _MonitorLog:
+    """``Monitor``'s results files (common/envs_utils.py:70-94, 172-194), written when ``log_dir`` is given
+    (make_env_fns, envs_utils.py:33-36): one ``<log_dir>/<rank>.monitor.csv`` per env -- a ``# {"t_start", "env_id"}`` JSON
+    header line, the CSV header ``r,l,t`` and one row per finished episode.  The reference holds one open file per worker
+    process; with thousands of envs in one process the rows are buffered and appended in batches (and on ``close``)."""
+    EXT = "monitor.csv"
+
+    def __init__(self, log_dir, first_env, n, env_id, t_start, flush_rows=8192):
+        self.dir, self.first, self.n, self.flush_rows = log_dir, first_env, n, flush_rows
+        os.makedirs(log_dir, exist_ok=True)
+        header = "# {} \n".format(json.dumps({"t_start": t_start, "env_id": env_id.split(":")[-1]})) + "r,l,t\r\n"
+        for i in range(n):
+            with open(self._path(i), "wt") as f:
+                f.write(header)
+        self.rows, self.count = {}, 0
+
+    def _path(self, i):
+        return os.path.join(self.dir, "%d.%s" % (self.first + i, self.EXT))
+
+    def write(self, idx, rs, ls, t):
+        for i, r, l in zip(idx.tolist(), rs, ls):
+            self.rows.setdefault(i, []).append("%s,%s,%s\r\n" % (r, l, t))     # csv.DictWriter's row format
+        self.count += len(rs)
+        if self.count >= self.flush_rows:
+            self.flush()
+
+    def flush(self):
+        for i, rows in self.rows.items():
+            with open(self._path(i), "at") as f:
+                f.write("".join(rows))
+        self.rows, self.count = {}, 0
+
+
+class _Infos(Sequence):
+    """``infos`` of a numpy-mode step: behaves like the tuple of N dicts ShmemVecEnv.step_wait returns (len, indexing,
+    iteration, the keys train.py:446-454 reads) without building 8192 references per step -- only the envs that finished
+    carry a dict of their own, every other position is one shared empty dict."""
+    __slots__ = ("_n", "_own")
+
+    def __init__(self, n, own):
+        self._n, self._own = n, own
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return tuple(self[k] for k in range(*i.indices(self._n)))
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._own.get(i, _NO_INFO)
+
+    def __iter__(self):
+        own = self._own
+        if not own:
+            return repeat(_NO_INFO, self._n)
+        return (own.get(i, _NO_INFO) for i in range(self._n))
+
+
+class _ArrayPool:
+    """Output arrays of the numpy-mode step.  The reference returns FRESH arrays every step (envs_utils.py:556-558,
+    608-620) and callers may keep them, so an array is handed out again only when nobody else holds a reference to it
+    (refcount check); otherwise a new one is allocated.  Why bother: a fresh 2 MB ``np.empty`` is an mmap whose pages
+    fault in while the C side unpacks into it and an munmap when it dies -- ~100 us per step at 8192 envs."""
+
+    def __init__(self, shape, dtype, depth=4):
+        self.shape, self.dtype, self.depth, self.items = shape, dtype, depth, []
+
+    def get(self):
+        for a in self.items:
+            if sys.getrefcount(a) == 3:           # the list's reference, the loop variable, getrefcount's argument
+                return a
+        a = np.empty(self.shape, self.dtype)
+        if len(self.items) < self.depth:
+            self.items.append(a)
+        return a
 
 
 class BatchedStepperEnv:
@@ -90,10 +175,17 @@ class BatchedStepperEnv:
         self.curriculum = 0
         self._table = None                                                  # uniform until a table is set
         N = self.num_envs
+        if log_dir and output == "torch":
+            raise NotImplementedError("log_dir (Monitor csv files) needs output='numpy': device mode keeps the episode "
+                                      "statistics on the device (steppingstone_b200.collector.EpisodeStats)")
+        self._monitor = _MonitorLog(log_dir, self.first_env, N, env_id, self._t0) if log_dir else None
         if output == "numpy":
             self._timeout = np.zeros(N, np.uint8)
             self._ep_ret = np.zeros(N, np.float32)
             self._ep_len = np.zeros(N, np.int32)
+            self._pool_obs = _ArrayPool((N, OBS_DIM), np.float32)
+            self._pool_rew = _ArrayPool((N,), np.float64)
+            self._pool_done = _ArrayPool((N,), np.bool_)
         else:
             import torch
             self._torch = torch
@@ -129,8 +221,9 @@ class BatchedStepperEnv:
             a = np.ascontiguousarray(actions, dtype=np.float32)
             assert a.shape == (self.num_envs, ACT_DIM)
             N = self.num_envs
-            # fresh arrays every step, as ShmemVecEnv._decode_obses / step_wait return (envs_utils.py:556-558, 608-620)
-            obs = np.empty((N, OBS_DIM), np.float32); rew = np.empty(N, np.float64); dones = np.empty(N, np.bool_)
+            # arrays nobody else refers to: fresh ones as far as the caller can tell (ShmemVecEnv._decode_obses / step_wait
+            # return new arrays every step, envs_utils.py:556-558, 608-620)
+            obs = self._pool_obs.get(); rew = self._pool_rew.get(); dones = self._pool_done.get()
             rc = self._lib.ss_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, dones.ctypes.data,
                                         self._timeout.ctypes.data, self._ep_ret.ctypes.data, self._ep_len.ctypes.data)
             if rc != 0:
@@ -138,9 +231,7 @@ class BatchedStepperEnv:
                 native.check(rc, "ss_step_host")
             # one shared empty dict for the envs that did not finish (train.py:446-454 only reads keys)
             idx = np.flatnonzero(dones)
-            if idx.size == 0:
-                return obs, rew, dones, self._no_infos
-            infos = list(self._no_infos)
+            own = {}
             if idx.size:                                                        # Monitor.update, envs_utils.py:136-151
                 t = round(time.time() - self._t0, 6)
                 rs = np.round(self._ep_ret[idx].astype(np.float64), 6).tolist()
@@ -149,8 +240,10 @@ class BatchedStepperEnv:
                     info = {"episode": {"r": r, "l": l, "t": t}}
                     if to:
                         info["bad_transition"] = True                           # TimeLimitMask, envs_utils.py:62-63
-                    infos[i] = info
-            return obs, rew, dones, tuple(infos)
+                    own[i] = info
+                if self._monitor is not None:
+                    self._monitor.write(idx, rs, ls, t)
+            return obs, rew, dones, _Infos(N, own)
         torch = self._torch
         a = actions
         if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()):
@@ -448,6 +541,8 @@ class BatchedStepperEnv:
         return int(self._lib.ss_launch_count(self._h))
 
     def close(self):
+        if getattr(self, "_monitor", None) is not None:
+            self._monitor.flush()
         if getattr(self, "_h", None):
             self._lib.ss_destroy(self._h)
             self._h = ctypes.c_void_p()

@@ -186,3 +186,45 @@ def test_robot_tables_match_the_reference_robot_classes():
             assert np.allclose(env.robot.body_xyz, T["init_pos"], atol=1e-9)
     finally:
         sys.path.remove(REF); sys.path.remove(fakes)
+
+
+def test_monitor_files_match_the_reference_writer(tmp_path):
+    """log_dir: `<log_dir>/<rank>.monitor.csv` with the header line, CSV header and row format of the reference's
+    Monitor / ResultsWriter (common/envs_utils.py:70-94, 172-194; make_env_fns :33-36) -- the parameter used to be accepted
+    and ignored (missing 7)."""
+    fakes = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fakes")
+    sys.path.insert(0, fakes); sys.path.insert(0, REF)
+    try:
+        from common.envs_utils import ResultsWriter
+    finally:
+        sys.path.remove(REF); sys.path.remove(fakes)
+    from steppingstone_b200.vec_env import _MonitorLog
+    ref_file = str(tmp_path / "ref" / "3")
+    os.makedirs(os.path.dirname(ref_file))
+    w = ResultsWriter(ref_file, header={"t_start": 12.5, "env_id": "Walker3DStepperEnv-v0"})
+    w.write_row({"r": 101.25, "l": 17, "t": 0.75}); w.write_row({"r": -3.5, "l": 1000, "t": 1.5}); w.f.close()
+    m = _MonitorLog(str(tmp_path / "ours"), 2, 3, "mocca_envs:Walker3DStepperEnv-v0", 12.5)
+    m.write(np.array([1]), [101.25], [17], 0.75); m.write(np.array([1, 2]), [-3.5, 8.0], [1000, 5], 1.5); m.flush()
+    assert sorted(os.listdir(tmp_path / "ours")) == ["2.monitor.csv", "3.monitor.csv", "4.monitor.csv"]
+    ours = open(tmp_path / "ours" / "3.monitor.csv", newline="").read()
+    assert ours == open(ref_file + ".monitor.csv", newline="").read()
+
+
+def test_lazy_infos_behave_like_the_reference_tuple():
+    """numpy-mode ``infos``: len / indexing / iteration / keys as the tuple of N dicts ShmemVecEnv.step_wait returns; the
+    consumer loop of train.py:446-454 runs on it unchanged."""
+    from steppingstone_b200.vec_env import _ArrayPool, _Infos
+    infos = _Infos(6, {1: {"episode": {"r": 2.0, "l": 9, "t": 0.1}}, 4: {"episode": {"r": 1.0, "l": 1000, "t": 0.2}, "bad_transition": True}})
+    bad_masks = np.ones((6, 1)); episode_rewards = []
+    for p_index, info in enumerate(infos):                      # train.py:446-454
+        keys = info.keys()
+        if "bad_transition" in keys:
+            bad_masks[p_index] = 0.0
+        if "episode" in keys:
+            episode_rewards.append(info["episode"]["r"])
+    assert bad_masks[:, 0].tolist() == [1, 1, 1, 1, 0, 1] and episode_rewards == [2.0, 1.0]
+    assert len(infos) == 6 and infos[-2]["bad_transition"] and infos[0] == {} and len(infos[1:3]) == 2
+    pool = _ArrayPool((8,), np.float32)
+    a = pool.get(); ida = id(a); del a
+    b = pool.get(); assert id(b) == ida                         # nobody kept the first array: it is handed out again
+    c = pool.get(); assert c is not b                           # b is still alive in the caller: a fresh array

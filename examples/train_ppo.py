@@ -81,7 +81,7 @@ class ActorCritic(nn.Module):
         self.logstd = nn.Parameter(torch.full((act_dim,), float(logstd)))  # DiagGaussian(noise=-1.5), controller.py:21
 
     def dist(self, obs):
-        return torch.distributions.Normal(torch.tanh(self.actor(obs)), self.logstd.exp())
+        return torch.distributions.Normal(torch.tanh(self.actor(obs)), self.logstd.exp(), validate_args=False)   # (validation syncs: not capturable)
 
     def act(self, obs, states, masks, deterministic=False):
         d = self.dist(obs)

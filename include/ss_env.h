@@ -84,13 +84,18 @@ int ss_step(ss_env* env, const float* act_dev, float* obs_dev, float* rew_dev, u
 
 /* Same call with HOST buffers (the reference's numpy-in / numpy-out contract, envs_utils.py:550-558, 608-620):
  * rew_host is float64 like the reference's stacked python floats, done_host / timeout_host are 0/1 bytes (numpy
- * bool storage).  A non-finite action fails with SS_ERR_ARG (robots.py:290: fatal in the reference too); slices of the
- * batch in front of it have already stepped.  Internally the batch
- * is pipelined in slices (H2D -> kernel -> one packed D2H per slice, unpacked on the host while later slices run);
- * returns after everything has landed in the caller's arrays. */
+ * bool storage).  One H2D copy of the actions, ONE launch over the batch; the kernel writes the observation rows and a
+ * 16-byte scalar record per env straight into pinned host memory -- into obs_host itself when that is pinned
+ * (ss_host_alloc / cudaHostAlloc / cudaHostRegister), else into a pinned buffer of the library's that is copied out.
+ * Returns after everything has landed in the caller's arrays.  A non-finite action fails with SS_ERR_ARG before anything
+ * runs (robots.py:290: fatal in the reference too, where the other workers have stepped by then). */
 int ss_step_host(ss_env* env, const float* act_host, float* obs_host, double* rew_host,
                  uint8_t* done_host, uint8_t* timeout_host, float* ep_ret_host, int32_t* ep_len_host);
 int ss_reset_host(ss_env* env, float* obs_host);
+/* pinned host memory for observation arrays the kernel can write into directly (no reference analogue: ShmemVecEnv's
+ * shared-memory observation buffers, envs_utils.py:507-513, play this role there) */
+int ss_host_alloc(size_t bytes, void** out);
+void ss_host_free(void* p);
 
 /* update_curriculum / update_specialist / update_sample_prob -- walker3d_envs.py:1346-1356, :604-622,
  * :1317-1320 (mike.py:856-866, :827-830) through envs_utils.py:568-586.  The caller passes the
@@ -176,7 +181,7 @@ int32_t ss_debug_floats(void);
 int ss_enable_debug(ss_env* env, int32_t on);
 int ss_debug_read(ss_env* env, float* out_host);
 
-/* host-side breakdown of the last ss_step_host (seconds): out4 = action copy + finite check, enqueue, waiting on the
+/* host-side breakdown of the last ss_step_host (seconds): out4 = action copy, enqueue, waiting on the
  * device, unpacking result records (bench.py reports it next to e2e) */
 int ss_host_timing(const ss_env* env, double* out4);
 int32_t ss_num_envs(const ss_env* env);

@@ -30,7 +30,7 @@ namespace ssb {
 #define SS_MINB 1
 #endif
 constexpr int WARPS_PER_BLOCK = SS_WPB;
-constexpr int SS_REC = 64;       // floats per env in the packed result record of the host-buffer path
+constexpr int SS_REC = 4;        // floats per env in the packed scalar record of the host-buffer path: reward, episode return, length, flags
 constexpr int BLOCK = 32 * WARPS_PER_BLOCK;
 
 struct alignas(16) BlockSmem {
@@ -521,9 +521,10 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
                                                          uint8_t* __restrict__ done, uint8_t* __restrict__ timeout,
                                                          float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int physics,
                                                          int e_begin, int e_end, float* __restrict__ packed) {
-    // envs [e_begin, e_end) of the batch (the host-buffer entry point pipelines the batch in slices).  packed != null:
-    // results go to one 256-byte record per env -- obs 60 f32, reward, episode return, episode length (int bits),
-    // done | timeout << 8 (int bits) -- so that a slice leaves the device in ONE copy.
+    // envs [e_begin, e_end) of the batch.  packed != null (host-buffer entry point): `obs` and `packed` are PINNED HOST
+    // memory the kernel writes straight into (zero-copy over PCIe, posted stores) -- the observation row in its final
+    // place, and one 16-byte record per env for the scalars: reward, episode return, episode length (int bits),
+    // done | timeout << 8 | non-finite action << 16 (int bits).
     BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
     stage_model_issue(B, gm);                  // the env's state row is fetched while the tables are in flight
     const DevModel& M = B.M;
@@ -639,7 +640,8 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     if (lane >= 6 && lane < ND) {                                                               // unclipped action (q5)
         a_again = act[(size_t)e * NJ + lane - 6];      // re-read (L1/L2 hit): keeps a register free through the physics
     }
-    if (__any_sync(FULL, !isfinite(a_again))) a_again = 0.f;           // non-finite action: stepped as zero (see the top)
+    const bool bad_act = __any_sync(FULL, !isfinite(a_again));
+    if (bad_act) a_again = 0.f;                                        // non-finite action: stepped as zero (see the top)
     m1 = fabsf(a_again * 0.1f * E.v_dof); m2 = a_again * a_again;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) { m1 += __shfl_xor_sync(FULL, m1, off); m2 += __shfl_xor_sync(FULL, m2, off); }
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     float r = progress - energy;
     r += step_bonus + target_bonus - 0.f;
     r += tall - posture - joints_pen;
-    float* o = packed ? packed + (size_t)e * SS_REC : obs + (size_t)e * SS_OBS;
+    float* o = obs + (size_t)e * SS_OBS;
     write_obs(W, E, o, lane);
     if (!physics) {
         if (lane == 0) { rew[e] = r; done[e] = dn ? 1 : 0; }
@@ -676,7 +678,8 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
         const int to = (d && E.elapsed == M.max_episode_steps) ? 1 : 0;
         const float er = (float)(rint(E.ep_ret * 1e6) / 1e6);
         if (packed) {
-            o[SS_OBS] = r; o[SS_OBS + 1] = er; o[SS_OBS + 2] = __int_as_float(E.ep_len); o[SS_OBS + 3] = __int_as_float((d ? 1 : 0) | (to << 8));
+            *reinterpret_cast<float4*>(packed + (size_t)e * SS_REC) =
+                make_float4(r, er, __int_as_float(E.ep_len), __int_as_float((d ? 1 : 0) | (to << 8) | (bad_act ? 1 << 16 : 0)));
         } else {
             rew[e] = r; done[e] = d ? 1 : 0; timeout[e] = to; ep_ret[e] = er; ep_len[e] = E.ep_len;
         }
@@ -925,7 +928,6 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(SS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int SS_PIPE = 4;        // slices per step of ss_step_host
 
 struct ss_env {
     int n = 0, device = 0, n_steps = 0, rendered = 0;
@@ -937,12 +939,11 @@ struct ss_env {
     size_t smem = 0;
     bool trace = false, debug = false;
     // host-buffer entry points: pinned staging + a pipeline of env slices on separate streams
-    float *h_act = nullptr, *h_rec = nullptr, *d_act = nullptr, *d_rec = nullptr;     // [N,21], [N,64]
+    float *h_act = nullptr, *h_rec = nullptr, *h_obs = nullptr, *d_act = nullptr;     // pinned [N,21], [N,4], [N,60]; device [N,21]
     cudaStream_t own = nullptr;
-    cudaStream_t pipe[SS_PIPE] = {};
-    double host_t[4] = {};           // last ss_step_host: action check, copy+enqueue, waiting on the device, unpacking (seconds)
+    double host_t[4] = {};           // last ss_step_host: action copy, enqueue, waiting on the device, unpacking (seconds)
     float* ts_base = nullptr; double* ts_ctx = nullptr;      // create_temp_states scratch
-    unsigned char* sort_keys = nullptr; int* sort_bins = nullptr;   // sort_envs scratch: [N] keys, SS_PIPE slots of 32 ints
+    unsigned char* sort_keys = nullptr; int* sort_bins = nullptr;   // sort_envs scratch: [N] keys, 64 ints
 };
 
 static void fill_model(DevModel& D, const ss_model& m, const ss_params& p) {
@@ -1071,7 +1072,7 @@ static int create_device_state(ss_env* E, const ss_model* model, const uint32_t*
     CK(cudaMalloc(&S.mt, N * 2 * SS_MT_WORDS * sizeof(uint32_t)));
     CK(cudaMalloc(&S.perm, N * sizeof(int)));
     CK(cudaMalloc(&S.err, sizeof(int))); CK(cudaMemset(S.err, 0, sizeof(int)));
-    CK(cudaMalloc(&E->sort_keys, N)); CK(cudaMalloc(&E->sort_bins, SS_PIPE * SORT_SLOT * sizeof(int)));
+    CK(cudaMalloc(&E->sort_keys, N)); CK(cudaMalloc(&E->sort_bins, SORT_SLOT * sizeof(int)));
     { std::vector<int> id(N); for (size_t i = 0; i < N; i++) id[i] = (int)i; CK(cudaMemcpy(S.perm, id.data(), N * sizeof(int), cudaMemcpyHostToDevice)); }
     CK(cudaMalloc(&E->cdf, (size_t)SS_GRID_CELLS * sizeof(double)));
     S.cdf = E->cdf;
@@ -1120,8 +1121,7 @@ void ss_destroy(ss_env* E) {
     DevState& S = E->S;
     cudaFree(E->dm); cudaFree(S.pos); cudaFree(S.sv); cudaFree(S.warm); cudaFree(S.terrain); cudaFree(S.plank);
     cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(S.perm); cudaFree(S.err); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.trace_ev); cudaFree(S.dbg);
-    cudaFreeHost(E->h_act); cudaFreeHost(E->h_rec); cudaFree(E->d_act); cudaFree(E->d_rec);
-    for (int k = 0; k < SS_PIPE; k++) if (E->pipe[k]) cudaStreamDestroy(E->pipe[k]);
+    cudaFreeHost(E->h_act); cudaFreeHost(E->h_rec); cudaFreeHost(E->h_obs); cudaFree(E->d_act);
     cudaFree(E->ts_base); cudaFree(E->ts_ctx); cudaFree(E->sort_keys); cudaFree(E->sort_bins);
     if (E->own) cudaStreamDestroy(E->own);
     delete E;
@@ -1140,7 +1140,7 @@ static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint
                        cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr, int slot = 0) {
     if (e_end < 0) e_end = E->n;
     if (physics == 1 && e_end - e_begin >= 4 * WARPS_PER_BLOCK) {
-        int* bins = E->sort_bins + SORT_SLOT * slot;
+        int* bins = E->sort_bins; (void)slot;
         const int nb = (e_end - e_begin + SORT_THREADS - 1) / SORT_THREADS;
         CK(cudaMemsetAsync(bins, 0, SORT_SLOT * sizeof(int), st));
         sort_hist_kernel<<<nb, SORT_THREADS, 0, st>>>(E->S, E->sort_keys, bins, e_begin, e_end);
@@ -1183,68 +1183,64 @@ int ss_env_post(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev,
 static int ensure_staging(ss_env* E) {
     if (E->h_act) return SS_OK;
     size_t N = (size_t)E->n;
-    CK(cudaMallocHost(&E->h_act, N * NJ * 4)); CK(cudaMallocHost(&E->h_rec, N * SS_REC * 4));
-    CK(cudaMalloc(&E->d_act, N * NJ * 4)); CK(cudaMalloc(&E->d_rec, N * SS_REC * 4));
-    for (int k = 0; k < SS_PIPE; k++) CK(cudaStreamCreateWithFlags(&E->pipe[k], cudaStreamNonBlocking));
+    CK(cudaMallocHost(&E->h_act, N * NJ * 4)); CK(cudaMallocHost(&E->h_rec, N * SS_REC * 4)); CK(cudaMallocHost(&E->h_obs, N * SS_OBS * 4));
+    CK(cudaMalloc(&E->d_act, N * NJ * 4));
     return SS_OK;
 }
 
-/* Host buffers in, host buffers out.  The batch is cut into up to SS_PIPE slices, each on its own stream: actions H2D ->
- * env_step_kernel on the slice -> ONE D2H of the slice's packed result records; while the GPU works on the later
- * slices the host unpacks the earlier ones into the caller's arrays, so only the last slice's copy-out is exposed. */
+/* Where the kernel writes the observations of a host-buffer call: straight into the caller's array when that is pinned
+ * host memory (ss_host_alloc, cudaHostAlloc, cudaHostRegister: device-accessible under unified addressing), else into the
+ * library's own pinned buffer, from which the rows are copied afterwards. */
+static float* obs_target(ss_env* E, float* obs, bool* direct) {
+    *direct = false;
+#ifndef SS_SIMT_EMU
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, obs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        *direct = true;
+        return static_cast<float*>(at.devicePointer);
+    }
+    cudaGetLastError();
+#endif
+    return E->h_obs;
+}
+
+/* Host buffers in, host buffers out.  actions: one copy into pinned memory + one H2D DMA; ONE launch over the whole batch
+ * (the sliced pipeline of round 1 paid four partial waves and 24 enqueues per step); the kernel writes observation rows and
+ * a 16-byte scalar record per env straight into pinned host memory, so nothing is copied back -- after the stream
+ * synchronises the host only widens the scalars into the caller's arrays. */
 int ss_step_host(ss_env* E, const float* act, float* obs, double* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el) {
     if (!E || !act || !obs || !rew || !done || !to || !er || !el) return fail(SS_ERR_ARG, "ss_step_host: null buffer");
     CK(cudaSetDevice(E->device));
     int rc = ensure_staging(E); if (rc) return rc;
     const int N = E->n;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t0 = now(), t_wait = 0, t_unpack = 0;
-    // Slices: equal shares except a short last one (its D2H + unpack is the only part not overlapped with GPU work).
-    const int nslice = N >= 4096 ? SS_PIPE : (N >= 1024 ? 2 : 1);
-    int b[SS_PIPE + 1];
-    {
-        static const int share[SS_PIPE + 1] = { 0, 28, 56, 84, 100 };      // cumulative percent, SS_PIPE == 4
-        for (int k = 0; k <= nslice; k++) {
-            int64_t cut = nslice == SS_PIPE ? (int64_t)N * share[k] / 100 : (int64_t)N * k / nslice;
-            b[k] = (int)(cut / WARPS_PER_BLOCK) * WARPS_PER_BLOCK;
-        }
-        b[nslice] = N;
-    }
-    double t1 = now();
-    // robots.py:290 `assert np.isfinite(a).all()` -- every worker of the reference asserts on ITS action inside step(), so a
-    // bad action is fatal there while other envs have already stepped.  Same here: each slice is checked on its way into
-    // the pinned buffer and launched at once (the GPU starts after the first slice, not after the whole batch); a
-    // non-finite action stops the call with SS_ERR_ARG, slices before it have stepped.
-    for (int k = 0; k < nslice; k++) {
-        cudaStream_t st = E->pipe[k];
-        const size_t n = (size_t)(b[k + 1] - b[k]), cnt = n * NJ;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(act) + (size_t)b[k] * NJ;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(E->h_act) + (size_t)b[k] * NJ;
+    const double t0 = now();
+    {   // robots.py:290 `assert np.isfinite(a).all()` while copying into the pinned buffer: refused before anything runs
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(act);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(E->h_act);
+        const size_t cnt = (size_t)N * NJ;
         uint32_t bad = 0;
-        for (size_t i = 0; i < cnt; i++) { uint32_t u = src[i]; dst[i] = u; bad |= (uint32_t)((u & 0x7f800000u) == 0x7f800000u); }
-        if (bad) {
-            for (int j = 0; j < k; j++) cudaStreamSynchronize(E->pipe[j]);
-            return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
-        }
-        CK(cudaMemcpyAsync(E->d_act + (size_t)b[k] * NJ, E->h_act + (size_t)b[k] * NJ, n * NJ * 4, cudaMemcpyHostToDevice, st));
-        rc = launch_step(E, E->d_act, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, 1, b[k], b[k + 1], E->d_rec, k); if (rc) return rc;
-        CK(cudaMemcpyAsync(E->h_rec + (size_t)b[k] * SS_REC, E->d_rec + (size_t)b[k] * SS_REC, n * SS_REC * 4, cudaMemcpyDeviceToHost, st));
+        for (size_t i = 0; i < cnt; i++) { const uint32_t u = src[i]; dst[i] = u; bad |= (uint32_t)((u & 0x7f800000u) == 0x7f800000u); }
+        if (bad) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
     }
-    double t2 = now();
-    for (int k = 0; k < nslice; k++) {
-        double ta = now();
-        CK(cudaStreamSynchronize(E->pipe[k]));
-        double tb = now(); t_wait += tb - ta;
-        for (int e = b[k]; e < b[k + 1]; e++) {
-            const float* r = E->h_rec + (size_t)e * SS_REC;
-            memcpy(obs + (size_t)e * SS_OBS, r, SS_OBS * 4);
-            int32_t len, flags; memcpy(&len, r + SS_OBS + 2, 4); memcpy(&flags, r + SS_OBS + 3, 4);
-            rew[e] = (double)r[SS_OBS]; er[e] = r[SS_OBS + 1]; el[e] = len;
-            done[e] = (uint8_t)(flags & 1); to[e] = (uint8_t)((flags >> 8) & 1);
-        }
-        t_unpack += now() - tb;
+    const double t1 = now();
+    bool direct; float* ot = obs_target(E, obs, &direct);
+    CK(cudaMemcpyAsync(E->d_act, E->h_act, (size_t)N * NJ * 4, cudaMemcpyHostToDevice, E->own));
+    rc = launch_step(E, E->d_act, ot, nullptr, nullptr, nullptr, nullptr, nullptr, E->own, 1, 0, N, E->h_rec); if (rc) return rc;
+    const double t2 = now();
+    CK(cudaStreamSynchronize(E->own));
+    const double t3 = now();
+    int32_t any = 0;
+    for (int e = 0; e < N; e++) {
+        const float* r = E->h_rec + (size_t)e * SS_REC;
+        int32_t len, flags; memcpy(&len, r + 2, 4); memcpy(&flags, r + 3, 4);
+        rew[e] = (double)r[0]; er[e] = r[1]; el[e] = len;
+        done[e] = (uint8_t)(flags & 1); to[e] = (uint8_t)((flags >> 8) & 1);
+        any |= flags;
     }
-    E->host_t[0] = t1 - t0; E->host_t[1] = t2 - t1; E->host_t[2] = t_wait; E->host_t[3] = t_unpack;
+    if (!direct) memcpy(obs, E->h_obs, (size_t)N * SS_OBS * 4);
+    E->host_t[0] = t1 - t0; E->host_t[1] = t2 - t1; E->host_t[2] = t3 - t2; E->host_t[3] = now() - t3;
+    if (any & (1 << 16)) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");      // (the kernel's own check; unreachable after the host's)
     return SS_OK;
 }
 
@@ -1252,14 +1248,20 @@ int ss_reset_host(ss_env* E, float* obs) {
     if (!E || !obs) return fail(SS_ERR_ARG, "ss_reset_host: null buffer");
     CK(cudaSetDevice(E->device));
     int rc = ensure_staging(E); if (rc) return rc;
-    const size_t N = (size_t)E->n;
-    // d_rec doubles as the [N,60] observation buffer of the reset
-    rc = ss_reset_all(E, E->d_rec, E->own); if (rc) return rc;
-    CK(cudaMemcpyAsync(E->h_rec, E->d_rec, N * SS_OBS * 4, cudaMemcpyDeviceToHost, E->own));
+    bool direct; float* ot = obs_target(E, obs, &direct);
+    rc = ss_reset_all(E, ot, E->own); if (rc) return rc;
     CK(cudaStreamSynchronize(E->own));
-    memcpy(obs, E->h_rec, N * SS_OBS * 4);
+    if (!direct) memcpy(obs, E->h_obs, (size_t)E->n * SS_OBS * 4);
     return SS_OK;
 }
+
+/* Pinned host memory for the caller's observation arrays (the kernel then writes into them directly). */
+int ss_host_alloc(size_t bytes, void** out) {
+    if (!out || !bytes) return fail(SS_ERR_ARG, "ss_host_alloc: bad argument");
+    CK(cudaMallocHost(out, bytes));
+    return SS_OK;
+}
+void ss_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int ss_set_sample_cdf(ss_env* E, const double* cdf, int32_t n_cells, int32_t apply_now, void* stream) {
     if (!E || !cdf || n_cells != SS_GRID_CELLS) return fail(SS_ERR_ARG, "ss_set_sample_cdf: table must have 11^5 cells");

@@ -90,6 +90,8 @@ _SIGNATURES = {
     "ss_step_injected": (ctypes.c_int, [_P] * 9),
     "ss_step_host": (ctypes.c_int, [_P] * 8),
     "ss_reset_host": (ctypes.c_int, [_P, _P]),
+    "ss_host_alloc": (ctypes.c_int, [ctypes.c_size_t, _P]),
+    "ss_host_free": (None, [_P]),
     "ss_set_sample_cdf": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
     "ss_update_tables": (ctypes.c_int, [_P, _P, _P, _P]),
     "ss_temp_state_cells": (ctypes.c_int64, [_I32]),

@@ -88,12 +88,26 @@ class _MonitorLog:
 
 class _Infos(Sequence):
     """``infos`` of a numpy-mode step: behaves like the tuple of N dicts ShmemVecEnv.step_wait returns (len, indexing,
-    iteration, the keys train.py:446-454 reads) without building 8192 references per step -- only the envs that finished
-    carry a dict of their own, every other position is one shared empty dict."""
-    __slots__ = ("_n", "_own")
+    iteration, the keys train.py:446-454 reads).  Nothing is built until somebody looks: only the envs that finished get
+    a dict of their own (``{"episode": {"r", "l", "t"}}`` from Monitor.update, envs_utils.py:136-151, plus
+    ``"bad_transition"`` from TimeLimitMask, :62-63), every other position is one shared empty dict."""
+    __slots__ = ("_n", "_raw", "_own")
 
-    def __init__(self, n, own):
-        self._n, self._own = n, own
+    def __init__(self, n, raw):
+        self._n, self._raw, self._own = n, raw, None
+
+    def _dicts(self):
+        if self._own is None:
+            own = {}
+            if self._raw is not None:
+                idx, rs, ls, tos, t = self._raw
+                for i, r, l, to in zip(idx, rs, ls, tos):
+                    info = {"episode": {"r": r, "l": l, "t": t}}
+                    if to:
+                        info["bad_transition"] = True
+                    own[i] = info
+            self._own = own
+        return self._own
 
     def __len__(self):
         return self._n
@@ -105,10 +119,10 @@ class _Infos(Sequence):
             i += self._n
         if not 0 <= i < self._n:
             raise IndexError(i)
-        return self._own.get(i, _NO_INFO)
+        return self._dicts().get(i, _NO_INFO)
 
     def __iter__(self):
-        own = self._own
+        own = self._dicts()
         if not own:
             return repeat(_NO_INFO, self._n)
         return (own.get(i, _NO_INFO) for i in range(self._n))
@@ -120,17 +134,44 @@ class _ArrayPool:
     (refcount check); otherwise a new one is allocated.  Why bother: a fresh 2 MB ``np.empty`` is an mmap whose pages
     fault in while the C side unpacks into it and an munmap when it dies -- ~100 us per step at 8192 envs."""
 
-    def __init__(self, shape, dtype, depth=4):
+    def __init__(self, shape, dtype, depth=4, factory=None):
         self.shape, self.dtype, self.depth, self.items = shape, dtype, depth, []
+        self.factory = factory or (lambda: np.empty(shape, dtype))
 
     def get(self):
         for a in self.items:
             if sys.getrefcount(a) == 3:           # the list's reference, the loop variable, getrefcount's argument
                 return a
-        a = np.empty(self.shape, self.dtype)
+        a = self.factory()
         if len(self.items) < self.depth:
             self.items.append(a)
         return a
+
+
+class _PinnedBlock:
+    """cudaHostAlloc'ed memory owned by a Python object (freed when the last array over it dies)."""
+
+    def __init__(self, lib, nbytes):
+        self.lib = lib
+        p = ctypes.c_void_p()
+        native.check(lib.ss_host_alloc(nbytes, ctypes.byref(p)), "ss_host_alloc")
+        self.ptr = p.value
+
+    def __del__(self):
+        try:
+            self.lib.ss_host_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def _pinned_array(lib, shape, dtype):
+    """A numpy array over pinned host memory: ``ss_step_host`` lets the kernel write the observations straight into it
+    (the role ShmemVecEnv's shared-memory observation buffers play in the reference, envs_utils.py:507-513)."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    blk = _PinnedBlock(lib, nbytes)
+    buf = (ctypes.c_char * nbytes).from_address(blk.ptr)
+    buf._blk = blk                              # array -> memoryview -> ctypes buffer -> block
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 class BatchedStepperEnv:
@@ -183,7 +224,7 @@ class BatchedStepperEnv:
             self._timeout = np.zeros(N, np.uint8)
             self._ep_ret = np.zeros(N, np.float32)
             self._ep_len = np.zeros(N, np.int32)
-            self._pool_obs = _ArrayPool((N, OBS_DIM), np.float32)
+            self._pool_obs = _ArrayPool((N, OBS_DIM), np.float32, factory=lambda: _pinned_array(self._lib, (N, OBS_DIM), np.float32))
             self._pool_rew = _ArrayPool((N,), np.float64)
             self._pool_done = _ArrayPool((N,), np.bool_)
         else:
@@ -205,7 +246,7 @@ class BatchedStepperEnv:
     def reset(self):
         """ShmemVecEnv.reset (envs_utils.py:542-548)."""
         if self.output == "numpy":
-            obs = np.empty((self.num_envs, OBS_DIM), np.float32)
+            obs = self._pool_obs.get()
             native.check(self._lib.ss_reset_host(self._h, obs.ctypes.data), "ss_reset_host")
             return obs
         native.check(self._lib.ss_reset_all(self._h, self._obs.data_ptr(), self._stream()), "ss_reset_all")
@@ -231,19 +272,15 @@ class BatchedStepperEnv:
                 native.check(rc, "ss_step_host")
             # one shared empty dict for the envs that did not finish (train.py:446-454 only reads keys)
             idx = np.flatnonzero(dones)
-            own = {}
+            raw = None
             if idx.size:                                                        # Monitor.update, envs_utils.py:136-151
                 t = round(time.time() - self._t0, 6)
                 rs = np.round(self._ep_ret[idx].astype(np.float64), 6).tolist()
-                ls = self._ep_len[idx].tolist(); tos = self._timeout[idx].tolist()
-                for i, r, l, to in zip(idx.tolist(), rs, ls, tos):
-                    info = {"episode": {"r": r, "l": l, "t": t}}
-                    if to:
-                        info["bad_transition"] = True                           # TimeLimitMask, envs_utils.py:62-63
-                    own[i] = info
+                ls = self._ep_len[idx].tolist()
+                raw = (idx.tolist(), rs, ls, self._timeout[idx].tolist(), t)
                 if self._monitor is not None:
                     self._monitor.write(idx, rs, ls, t)
-            return obs, rew, dones, _Infos(N, own)
+            return obs, rew, dones, _Infos(N, raw)
         torch = self._torch
         a = actions
         if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()):

@@ -533,9 +533,10 @@ def test_set_env_and_robot_params():
 
 
 def test_host_pipeline_matches_device_mode():
-    """ss_step_host cuts large batches into slices on separate streams (packed result records, unpacked on the host while
-    later slices run): bit-identical to the single-launch device path, ragged last slice included; a non-finite action
-    is refused before anything runs (robots.py:290)."""
+    """ss_step_host (host arrays in and out: one H2D copy of the actions, one launch, observation rows and scalar records
+    written by the kernel straight into pinned host memory) is bit-identical to the device path, ragged last CTA
+    included; the arrays handed out are fresh as far as the caller can tell; a non-finite action is refused before
+    anything runs (robots.py:290)."""
     import torch
     n = 4100 + 7
     gh = make_gpu_env(1, n); gd = make_gpu_env(1, n, output="torch")
@@ -548,6 +549,10 @@ def test_host_pipeline_matches_device_mode():
         oh, rh, dh, ih = gh.step(a)
         od, rd, dd, idv = gd.step(torch.tensor(a, device="cuda"))
         assert oh.dtype == np.float32 and rh.dtype == np.float64 and dh.dtype == np.bool_ and len(ih) == n
+        if t == 3:
+            kept = [oh, oh.copy()]                                     # the caller keeps an array: it must never be written again
+        if t > 3:
+            assert np.array_equal(kept[0], kept[1])
         assert np.array_equal(oh, od.cpu().numpy())
         assert np.array_equal(rh.astype(np.float32), rd.cpu().numpy())
         assert np.array_equal(dh, dd.cpu().numpy().astype(bool))
@@ -561,11 +566,10 @@ def test_host_pipeline_matches_device_mode():
         gh.step(a)
     after = gh.get_state()
     assert np.array_equal(before["q"], after["q"]) and np.array_equal(before["ints"], after["ints"])
-    # a bad action in the LAST slice is refused too (the slices in front of it have stepped by then, as the workers of
-    # the reference would have: robots.py:290 asserts inside each worker's step)
-    a[5, 3] = 0.0; a[n - 1, 20] = np.inf
+    a[5, 3] = 0.0; a[n - 1, 20] = np.inf                       # ... wherever it sits in the batch
     with pytest.raises(AssertionError):
         gh.step(a)
+    assert np.array_equal(before["q"], gh.get_state()["q"])
 
 
 @pytest.mark.parametrize("kind", KINDS)

@@ -214,7 +214,7 @@ def test_lazy_infos_behave_like_the_reference_tuple():
     """numpy-mode ``infos``: len / indexing / iteration / keys as the tuple of N dicts ShmemVecEnv.step_wait returns; the
     consumer loop of train.py:446-454 runs on it unchanged."""
     from steppingstone_b200.vec_env import _ArrayPool, _Infos
-    infos = _Infos(6, {1: {"episode": {"r": 2.0, "l": 9, "t": 0.1}}, 4: {"episode": {"r": 1.0, "l": 1000, "t": 0.2}, "bad_transition": True}})
+    infos = _Infos(6, ([1, 4], [2.0, 1.0], [9, 1000], [0, 1], 0.2))
     bad_masks = np.ones((6, 1)); episode_rewards = []
     for p_index, info in enumerate(infos):                      # train.py:446-454
         keys = info.keys()

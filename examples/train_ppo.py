@@ -85,7 +85,8 @@ class ActorCritic(nn.Module):
 
     def act(self, obs, states, masks, deterministic=False):
         d = self.dist(obs)
-        a = d.mean if deterministic else d.sample()
+        # (d.sample() is torch.normal with a tensor std, which checks std >= 0 on the host: not capturable in a CUDA graph)
+        a = d.mean if deterministic else d.mean + d.stddev * torch.randn_like(d.mean)
         return self.critic(obs), a, d.log_prob(a).sum(-1, keepdim=True), states
 
     def get_value(self, obs, states, masks):

@@ -68,7 +68,7 @@ class ActorCritic(nn.Module):
     """Policy.act / get_value / evaluate_actions (common/controller.py:106-150).  ``arch="reference"``: the shipped
     policies' SoftsignActor; ``"small"``: a 3-hidden-layer ReLU actor (faster, the default of the earlier logs)."""
 
-    def __init__(self, obs_dim, act_dim, h=256, arch="small", logstd=-1.5, out_gain=1.0):
+    def __init__(self, obs_dim, act_dim, h=256, arch="small", logstd=-1.5, out_gain=1.0, fixed_logstd=False):
         super().__init__()
         if arch == "reference":
             self.actor = SoftsignActor(obs_dim, act_dim, h)
@@ -78,7 +78,7 @@ class ActorCritic(nn.Module):
         else:
             self.actor = mlp([obs_dim, h, h, h, act_dim], nn.ReLU, nn.init.calculate_gain("relu"), out_gain)
         self.critic = mlp([obs_dim, h, h, h, h, 1], nn.ReLU, nn.init.calculate_gain("relu"))
-        self.logstd = nn.Parameter(torch.full((act_dim,), float(logstd)))  # DiagGaussian(noise=-1.5), controller.py:21
+        self.logstd = nn.Parameter(torch.full((act_dim,), float(logstd)), requires_grad=not fixed_logstd)  # DiagGaussian(noise=-1.5), controller.py:21
 
     def dist(self, obs):
         return torch.distributions.Normal(torch.tanh(self.actor(obs)), self.logstd.exp(), validate_args=False)   # (validation syncs: not capturable)
@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--reward-scale", type=float, default=1.0, help="rewards are multiplied by this before GAE (returns of ~500 -> O(5) for the critic)")
     ap.add_argument("--kl-target", type=float, default=0.0, help="> 0: adapt the lr to keep the per-update KL near this (x1.5 / /1.5), instead of --lr-decay")
     ap.add_argument("--out-gain", type=float, default=1.0, help="scale of the actor's last layer at initialisation (0.01: near-zero initial actions)")
+    ap.add_argument("--fixed-logstd", action="store_true", help="keep the exploration noise at --logstd instead of learning it (it otherwise collapses once the policy has found how to stand)")
     ap.add_argument("--graph", action="store_true", help="collect each rollout by replaying ONE CUDA graph (collector.GraphedRollout)")
     ap.add_argument("--tf32", action="store_true", help="TF32 matmuls in the policy / update (the env is unaffected)")
     ap.add_argument("--gamma", type=float, default=0.99)
@@ -180,12 +181,12 @@ def main():
         envs.update_curriculum(args.curriculum)
     if args.init_actor:
         args.arch = "reference"
-    ac = ActorCritic(60, 21, arch=args.arch, logstd=args.logstd, out_gain=args.out_gain).to(dev)
+    ac = ActorCritic(60, 21, arch=args.arch, logstd=args.logstd, out_gain=args.out_gain, fixed_logstd=args.fixed_logstd).to(dev)
     if args.init_actor:
         ac.actor.load_npz(args.init_actor)
     if distributed:
         sharding.broadcast_parameters(ac)
-    opt = torch.optim.Adam(ac.parameters(), lr=args.lr, eps=1e-5)
+    opt = torch.optim.Adam([p_ for p_ in ac.parameters() if p_.requires_grad], lr=args.lr, eps=1e-5)
     rollouts = RolloutStorage(args.steps, args.envs, (60,), 21, 1, device=dev)
     rollouts.observations[0].copy_(envs.reset())
     num_mini_batch = max(1, args.envs * args.steps // args.mini_batch)
@@ -238,8 +239,8 @@ def main():
                 reached[(mark, curriculum)] = (time.time() - t_start, frames)
         if rank == 0:
             line = ("iter %4d t %6.1fs frames %11d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  stones/1000steps %5.2f  "
-                    "value_loss %9.4f  kl %.4f  curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy, %d GPU)  update %.2fs" % (
-                        it, time.time() - t_start, frames, n_ep, mean_r, mean_l, rew_mean, stones, vl, kl, curriculum, lr,
+                    "value_loss %9.4f  kl %.4f  logstd %.2f  curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy, %d GPU)  update %.2fs" % (
+                        it, time.time() - t_start, frames, n_ep, mean_r, mean_l, rew_mean, stones, vl, kl, float(ac.logstd.mean()), curriculum, lr,
                         world * args.envs * args.steps / (t1 - t0), world, t2 - t1))
             print(line, flush=True)
             if logf:

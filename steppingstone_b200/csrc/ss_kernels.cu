@@ -1040,6 +1040,10 @@ int ss_create(const ss_model* model, const ss_params* params, int32_t n, int32_t
     E->n = n; E->device = device; E->n_steps = params->n_steps; E->rendered = params->rendered;
     fill_model(E->hm, *model, *params);
     E->smem = sizeof(BlockSmem);
+    if (const char* pad = getenv("SS_SMEM_PAD")) {          // experiments only: force one CTA per SM for small-CTA builds (occupancy scans)
+        const size_t want = (size_t)atol(pad);
+        if (want > E->smem && want <= 232448) E->smem = want;
+    }
     int rc = configure_kernels(E->smem);
     if (!rc) rc = create_device_state(E, model, mt_env, mt_aux);
     if (rc) {                                    // e.g. out of memory half-way: release what was allocated, keep the message

@@ -866,6 +866,65 @@ __device__ __forceinline__ int collide_warp(const DevModel& M, WarpSmem& W, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Projected Gauss-Seidel in constraint space (btMultiBodyConstraintSolver::solveSingleIteration order: limit rows in
+// alternating direction, then all normals, then all friction rows), lane = row, Delassus row in registers.
+//   Every lane evaluates its own row update each row step (branch-free); the owner of row RR publishes its impulse
+//   change with one shuffle and all lanes fold it into their accumulator c = lam (1 - cfm) + rhs - (J dv) / D.
+//   Contact normals (lo = 0, hi = "infinity") keep e = c - lam instead of c: the impulse change is max(e, -lam), one
+//   FMNMX and no subtraction on the dependent chain; their diagonal coefficient carries +cfm instead of -(1 - cfm).
+//   Friction bounds depend on the normal impulse, which only changes in the normal block: one shuffle per iteration.
+//   NC = number of contacts (exact): rows 0..NC-1 normals, MAXC + 2c, MAXC + 2c + 1 the friction rows of contact c.
+// ---------------------------------------------------------------------------------------------
+#define SS_ROW_STEP(RR)                                                        \
+        {                                                                      \
+            float sum_ = fminf(fmaxf(c, lo_c), hi_c);                          \
+            float dl_ = shfl(sum_ - lam, (RR));                                \
+            lam = (lane == (RR)) ? sum_ : lam;                                 \
+            c = fmaf(-Ar[(RR)], dl_, c);                                       \
+        }
+#define SS_NORMAL_STEP(RR)                                                     \
+        {                                                                      \
+            float d_ = fmaxf(c, -lam);                                         \
+            float dl_ = shfl(d_, (RR));                                        \
+            lam = (lane == (RR)) ? lam + d_ : lam;                             \
+            c = fmaf(-Ar[(RR)], dl_, c);                                       \
+        }
+template <bool DIAG, int NC>
+__device__ __forceinline__ void pgs_solve(const float (&Ar)[32], float& c, float& lam, float& lo_c, float& hi_c, const int nl,
+                                          const int n_iters, const bool isfric, const int nsrc, const float mu, const int lane,
+                                          unsigned* push_hist) {
+    // warm start: fold the cached normal impulses in (dv = sum_s W_s lam_s)
+#pragma unroll
+    for (int k = 0; k < NC; k++) { const float l0 = shfl(lam, k); c = fmaf(-Ar[k], l0, c); }
+    for (int it = 0; it < n_iters; it++) {
+        if (it & 1) {
+#pragma unroll
+            for (int k = 0; k < MAXL; k += 2)
+                if (nl > k) { SS_ROW_STEP(3 * MAXC + k); SS_ROW_STEP(3 * MAXC + k + 1); }
+        } else {
+#pragma unroll
+            for (int k = MAXL - 2; k >= 0; k -= 2)
+                if (nl > k) { SS_ROW_STEP(3 * MAXC + k + 1); SS_ROW_STEP(3 * MAXC + k); }
+        }
+        if constexpr (NC > 0) {
+#pragma unroll
+            for (int k = 0; k < NC; k++) SS_NORMAL_STEP(k);
+            const float ln = shfl(lam, nsrc);
+            if (isfric) { const bool live = ln > 0.f; hi_c = live ? mu * ln : lam; lo_c = live ? -hi_c : lam; }
+            // friction rows of a contact that does not push are no-ops (bounds pinned to the current impulse; Bullet skips
+            // them too: `if (totalImpulse > 0)` in solveSingleIteration): skipped, warp-uniformly
+            const unsigned pushing = __ballot_sync(FULL, lam > 0.f) & ((1u << MAXC) - 1u);
+            if (DIAG && push_hist && it < 31) *push_hist |= ((pushing >> (lane & (MAXC - 1))) & 1u) << it;   // lane = contact (parity probe)
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                if ((pushing >> k) & 1u) { SS_ROW_STEP(MAXC + 2 * k); SS_ROW_STEP(MAXC + 2 * k + 1); }
+        }
+    }
+}
+#undef SS_ROW_STEP
+#undef SS_NORMAL_STEP
+
+// ---------------------------------------------------------------------------------------------
 // one physics substep.  State in registers: quat (all lanes), q_dof / v_dof (lane = dof), dpos =
 // displacement of the base since the start of the control step (all lanes), warm (lane = candidate slot).
 // Returns the per-foot contact flags of this substep's collision pass (bit f).
@@ -1110,56 +1169,20 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         // friction rows start dead (bounds pinned to the current impulse => no change) until their normal pushes
         float lo_c = isfric ? lam : lo, hi_c = isfric ? lam : hi;
         float c = rhs;
-#define SS_ROW_STEP(RR)                                                        \
-        {                                                                      \
-            float sum_ = fminf(fmaxf(c, lo_c), hi_c);                          \
-            float dl_ = shfl(sum_ - lam, (RR));                                \
-            lam = (lane == (RR)) ? sum_ : lam;                                 \
-            c = fmaf(-Ar[(RR)], dl_, c);                                       \
+        // warm start + the 20 iterations, in a copy specialised for the EXACT number of contacts (compile-time row
+        // indices, no per-row-pair count checks: they were 240 uniform compare + branch pairs per substep, and a contact
+        // count that is odd no longer pays a dead normal step and two dead friction steps per iteration)
+        switch (nc) {
+            case 0: pgs_solve<DIAG, 0>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            case 1: pgs_solve<DIAG, 1>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            case 2: pgs_solve<DIAG, 2>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            case 3: pgs_solve<DIAG, 3>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            case 4: pgs_solve<DIAG, 4>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            case 5: pgs_solve<DIAG, 5>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            case 6: pgs_solve<DIAG, 6>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            case 7: pgs_solve<DIAG, 7>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
+            default: pgs_solve<DIAG, 8>(Ar, c, lam, lo_c, hi_c, nl, M.n_iters, isfric, nsrc, mu, lane, push_hist); break;
         }
-        // contact normals (lo = 0, hi = "infinity") keep e = c - lam instead of c: the impulse change is max(e, -lam),
-        // one FMNMX and no subtraction on the dependent chain; their diagonal coefficient carries +cfm instead of -(1 - cfm)
-#define SS_NORMAL_STEP(RR)                                                     \
-        {                                                                      \
-            float d_ = fmaxf(c, -lam);                                         \
-            float dl_ = shfl(d_, (RR));                                        \
-            lam = (lane == (RR)) ? lam + d_ : lam;                             \
-            c = fmaf(-Ar[(RR)], dl_, c);                                       \
-        }
-        // warm start: fold the cached normal impulses in (dv = sum_s W_s lam_s)
-#pragma unroll
-        for (int k = 0; k < MAXC; k += 2)
-            if (nc > k) {
-                float l0 = shfl(lam, k), l1 = shfl(lam, k + 1);
-                c = fmaf(-Ar[k], l0, c); c = fmaf(-Ar[k + 1], l1, c);
-            }
-        for (int it = 0; it < M.n_iters; it++) {
-            if (it & 1) {
-#pragma unroll
-                for (int k = 0; k < MAXL; k += 2)
-                    if (nl > k) { SS_ROW_STEP(3 * MAXC + k); SS_ROW_STEP(3 * MAXC + k + 1); }
-            } else {
-#pragma unroll
-                for (int k = MAXL - 2; k >= 0; k -= 2)
-                    if (nl > k) { SS_ROW_STEP(3 * MAXC + k + 1); SS_ROW_STEP(3 * MAXC + k); }
-            }
-#pragma unroll
-            for (int k = 0; k < MAXC; k += 2)
-                if (nc > k) { SS_NORMAL_STEP(k); SS_NORMAL_STEP(k + 1); }
-            float ln = shfl(lam, nsrc);
-            if (isfric) { bool live = ln > 0.f; hi_c = live ? mu * ln : lam; lo_c = live ? -hi_c : lam; }
-            // friction rows of a contact that does not push are no-ops (bounds pinned to the current impulse; Bullet skips
-            // them too: `if (totalImpulse > 0)` in solveSingleIteration): skip the pair's four row steps, warp-uniformly
-            const unsigned pushing = __ballot_sync(FULL, lam > 0.f) & ((1u << MAXC) - 1u);
-            if (DIAG && push_hist && it < 31) *push_hist |= ((pushing >> (lane & (MAXC - 1))) & 1u) << it;   // lane = contact (parity probe)
-#pragma unroll
-            for (int k = 0; k < MAXC; k += 2)
-                if ((pushing >> k) & 3u) {
-                    SS_ROW_STEP(MAXC + 2 * k); SS_ROW_STEP(MAXC + 2 * k + 1); SS_ROW_STEP(MAXC + 2 * k + 2); SS_ROW_STEP(MAXC + 2 * k + 3);
-                }
-        }
-#undef SS_ROW_STEP
-#undef SS_NORMAL_STEP
         if (DIAG && dbg) dbg[DBG_ROWS + 4 + lane * 6 + 5] = lam;
         // ---- velocity update: dv = L^-T D^-1 sum_r z_r lam_r ----
         __syncwarp();

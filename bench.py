@@ -156,6 +156,10 @@ def exchange_block(env, dev, world, rank, N, T, acts):
     ok = ok and bool(torch.equal(chk, ref))
     del g
     torch.cuda.empty_cache()
+    ms_r, g = timed(lambda: sharding.gather_rollout(ro, rank_major=True))          # no env-axis transpose: [world, T+1, N, .]
+    ok = ok and tuple(g["observations"].shape) == (world, T + 1, N, 60) and bool(torch.equal(g["rewards"][rank], ro.rewards))
+    del g
+    torch.cuda.empty_cache()
     # (b) data-parallel alternative: advantage statistics + gradient all-reduce of the reference's actor + critic (~0.5 M parameters)
     adv = ro.returns[:-1] - ro.value_preds[:-1]
     sharding.global_advantage_stats(adv)
@@ -170,7 +174,10 @@ def exchange_block(env, dev, world, rank, N, T, acts):
             "fill_s": fill_s, "fill_env_steps_per_s": world * N * T / fill_s, "gae_ms": gae_ms, "verified": ok,
             "gather": {"collective": "ncclAllGather (all_gather_into_tensor per field, 9 fields) + one strided copy per field",
                        "bytes_received_per_rank": out_bytes, "ms": ms_g, "GBps_into_each_rank": out_bytes / ms_g / 1e6,
-                       "nvlink5_per_direction_GBps": 900.0, "frac_of_nvlink": out_bytes * (world - 1) / world / ms_g / 1e6 / 900.0},
+                       "nvlink5_per_direction_GBps": 900.0, "frac_of_nvlink": out_bytes * (world - 1) / world / ms_g / 1e6 / 900.0,
+                       "rank_major_ms": ms_r, "rank_major_GBps_into_each_rank": out_bytes / ms_r / 1e6,
+                       "rank_major_frac_of_nvlink": out_bytes * (world - 1) / world / ms_r / 1e6 / 900.0,
+                       "rank_major_note": "gathered buffers kept [world, T+1, N, .] (no strided copy): what a PPO update that flattens (time, env) needs"},
             "data_parallel": {"collective": "ncclAllReduce", "advantage_stats_ms": ms_adv, "grad_allreduce_ms": ms_gr,
                               "grad_bytes": n_param * 4, "allreduces_per_update": n_mb, "per_update_ms": ms_adv + n_mb * ms_gr}}
 

@@ -30,11 +30,15 @@ def make_sharded_vec_envs(env_id, seed, n_total, rank=None, world=None, **kwargs
 ROLLOUT_FIELDS = ("observations", "states", "rewards", "value_preds", "returns", "action_log_probs", "actions", "masks", "bad_masks")
 
 
-def gather_rollout(rollouts, group=None, fields=ROLLOUT_FIELDS):
-    """All-gather the [T(+1), N_local, ...] rollout tensors along the env axis -> dict of [T(+1), N_total, ...].
+def gather_rollout(rollouts, group=None, fields=ROLLOUT_FIELDS, rank_major=False):
+    """All-gather the [T(+1), N_local, ...] rollout tensors over the ranks.
     Shards must be equal-sized (N_total divisible by the world size), as in BASELINE config 4 (8 x 8192).
     One ``all_gather_into_tensor`` per field into a [world, T, N_local, ...] buffer (NCCL writes every peer's shard
-    straight into place), then one strided copy to put the env axis second."""
+    straight into place).  Default: one more strided copy puts the env axis second -> dict of [T(+1), N_total, ...], the
+    shapes a single-process RolloutStorage of N_total envs would have.  ``rank_major=True`` returns the gathered buffers as
+    they are, [world, T(+1), N_local, ...]: the PPO update only ever flattens (time, env) into one sample axis and
+    permutes it (storage.py:84-103), so it can consume them without that copy (half the time, no second 32 GB buffer at
+    T = 2048)."""
     world = dist.get_world_size(group)
     out = {}
     for name in fields:
@@ -44,7 +48,7 @@ def gather_rollout(rollouts, group=None, fields=ROLLOUT_FIELDS):
             dist.all_gather_into_tensor(buf, t, group=group)
         else:                                         # gloo (CPU tests): list form
             dist.all_gather(list(buf.unbind(0)), t, group=group)
-        out[name] = buf.transpose(0, 1).reshape(t.shape[0], world * t.shape[1], *t.shape[2:])
+        out[name] = buf if rank_major else buf.transpose(0, 1).reshape(t.shape[0], world * t.shape[1], *t.shape[2:])
     return out
 
 

@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--graph", action="store_true", help="collect each rollout by replaying ONE CUDA graph (collector.GraphedRollout)")
     ap.add_argument("--tf32", action="store_true", help="TF32 matmuls in the policy / update (the env is unaffected)")
     ap.add_argument("--gamma", type=float, default=0.99)
-    ap.add_argument("--log", default=None, help="rank 0 also appends its iteration lines to this file")
+    ap.add_argument("--logfile", default=None, help="rank 0 also appends its iteration lines to this file")
     args = ap.parse_args()
     if args.tf32:
         torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
@@ -197,7 +197,7 @@ def main():
     if runner is not None:
         frames += args.envs * args.steps * world          # the capture's warm-up rollout (its data is discarded)
     lr = args.lr
-    logf = open(args.log, "a") if (args.log and rank == 0) else None
+    logf = open(args.logfile, "a") if (args.logfile and rank == 0) else None
     reached = {}                                          # first time / frames at which the mean return passed a mark
     for it in range(args.iters):
         if not args.kl_target:

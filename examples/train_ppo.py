@@ -158,7 +158,11 @@ def main():
     ap.add_argument("--fixed-logstd", action="store_true", help="keep the exploration noise at --logstd instead of learning it (it otherwise collapses once the policy has found how to stand)")
     ap.add_argument("--graph", action="store_true", help="collect each rollout by replaying ONE CUDA graph (collector.GraphedRollout)")
     ap.add_argument("--tf32", action="store_true", help="TF32 matmuls in the policy / update (the env is unaffected)")
-    ap.add_argument("--gamma", type=float, default=0.99)
+    ap.add_argument("--gamma", type=float, default=0.99,
+                    help="discount (train.py:78: 0.99).  With the large batches of this trainer 0.99 settles on STANDING (the alive bonus of 2 per "
+                         "step outweighs the risk of a first step); 0.95-0.97 learns to walk within a minute (profiles/r02m_*)")
+    ap.add_argument("--gamma-final", type=float, default=None, help="anneal the discount linearly to this value ...")
+    ap.add_argument("--gamma-anneal", type=int, nargs=2, default=(0, 0), metavar=("START", "LEN"), help="... from iteration START over LEN iterations")
     ap.add_argument("--logfile", default=None, help="rank 0 also appends its iteration lines to this file")
     args = ap.parse_args()
     if args.tf32:
@@ -216,7 +220,10 @@ def main():
             rollouts.rewards.mul_(args.reward_scale)
         with torch.no_grad():
             next_value = ac.get_value(rollouts.observations[-1], None, None)
-        rollouts.compute_returns(next_value, True, args.gamma, 0.95)
+        gamma = args.gamma
+        if args.gamma_final is not None and args.gamma_anneal[1] > 0:
+            gamma += (args.gamma_final - args.gamma) * min(1.0, max(0.0, (it - args.gamma_anneal[0]) / args.gamma_anneal[1]))
+        rollouts.compute_returns(next_value, True, gamma, 0.95)
         torch.cuda.synchronize(); t1 = time.time()
         vl, al, kl = ppo_update(ac, opt, rollouts, args.epochs, num_mini_batch, distributed=distributed,
                                 actor_frozen=it < args.critic_warmup)
@@ -239,8 +246,8 @@ def main():
                 reached[(mark, curriculum)] = (time.time() - t_start, frames)
         if rank == 0:
             line = ("iter %4d t %6.1fs frames %11d  episodes %6d  mean_return %8.2f  mean_len %6.1f  rew/step %6.3f  stones/1000steps %5.2f  "
-                    "value_loss %9.4f  kl %.4f  logstd %.2f  curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy, %d GPU)  update %.2fs" % (
-                        it, time.time() - t_start, frames, n_ep, mean_r, mean_l, rew_mean, stones, vl, kl, float(ac.logstd.mean()), curriculum, lr,
+                    "value_loss %9.4f  kl %.4f  logstd %.2f  gamma %.3f  curriculum %d  lr %.1e  collect %.0f env-steps/s (incl. policy, %d GPU)  update %.2fs" % (
+                        it, time.time() - t_start, frames, n_ep, mean_r, mean_l, rew_mean, stones, vl, kl, float(ac.logstd.mean()), gamma, curriculum, lr,
                         world * args.envs * args.steps / (t1 - t0), world, t2 - t1))
             print(line, flush=True)
             if logf:

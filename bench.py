@@ -603,10 +603,23 @@ def run_b200(args, wl):
     peak, peak_src = measured_peaks()
     kern_s = t_dev / K
     achieved = ALG_BYTES_PER_ENV_STEP * N / kern_s / 1e9
-    traffic = None
+    # DRAM traffic and the compute-side numbers come from ONE committed `ncu --set full` capture of this kernel
+    # (tools/final_evidence.sh -> tools/ncu_summary.py -> profiles/traffic.json, which names the capture and the git head it
+    # was taken at): nothing measured under a profiler is a bench value, and a stale capture is visible as such.
+    traffic, compute = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("env_step_kernel_dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("env_step_kernel_dram_bytes_per_launch")
+        compute = {"kernel": "env_step_kernel", "bound": "fp32 issue / dependent latency (SURVEY 8d)",
+                   "issue_active_pct": tj.get("issue_active_pct"), "pipe_fma_pct_of_peak": tj.get("pipe_fma_pct_of_peak"),
+                   "pipe_alu_pct_of_peak": tj.get("pipe_alu_pct_of_peak"),
+                   "warp_instructions_per_env_substep": tj.get("warp_instructions_per_env_substep"),
+                   "traffic_over_algorithmic": tj.get("traffic_over_algorithmic"),
+                   "local_memory_instructions_per_launch": (tj.get("local_load_instructions") or 0) + (tj.get("local_store_instructions") or 0),
+                   "registers_per_thread": tj.get("registers_per_thread"), "stall_per_issue": tj.get("stall_per_issue"),
+                   "capture": tj.get("capture"), "capture_git_head": tj.get("git_head"),
+                   "note": "from the committed ncu capture (not measured in this run); issue-slot utilisation is the meaningful roofline of this kernel"}
     aba_achieved = ALG_BYTES_PER_ENV_SUBSTEP * N / aba_s / 1e9
 
     if rank == 0:
@@ -643,6 +656,8 @@ def run_b200(args, wl):
                                              "achieved": ALG_BYTES_PER_ENV_SUBSTEP * NL / abaL_s / 1e9,
                                              "frac": ALG_BYTES_PER_ENV_SUBSTEP * NL / abaL_s / 1e9 / peak}},
         }
+        if compute is not None:
+            line["roofline_compute"] = compute
         if tsf is not None:
             if "achieved" in tsf:
                 tsf.update(kernel="temp_prep_kernel + temp_fill_kernel", bound="hbm", peak=peak, unit="GB/s", frac=tsf["achieved"] / peak,

@@ -17,6 +17,7 @@
 #ifndef SS_ENV_H
 #define SS_ENV_H
 #include <stdint.h>
+#include <stddef.h>
 #include "ss_model.h"
 
 #ifdef __cplusplus
@@ -33,6 +34,7 @@ extern "C" {
 #define SS_NINT 8        /* int32 per env in ss_state_view.ints                                   */
 #define SS_NEV 18        /* int32 per env and substep in the discrete-event trace (ss_substep_events)   */
 #define SS_MT_WORDS 625  /* MT19937: 624 state words + position                                   */
+#define SS_TABLE_RING 8  /* sampling-table versions kept alive (ss_set_sample_cdf)                  */
 
 /* scalars[]: */
 enum { SS_S_POTENTIAL = 0, SS_S_WALK_X, SS_S_WALK_Y, SS_S_WALK_Z, SS_S_INITIAL_Z,
@@ -53,6 +55,7 @@ typedef struct ss_state_view {
     double* scalars;   /* [N,SS_NSCAL]                                                            */
     int32_t* ints;     /* [N,SS_NINT]                                                             */
     uint32_t* mt;      /* [N,2,SS_MT_WORDS] env np_random stream, then the env's aux stream (see ss_create)      */
+    int32_t* table_slot; /* [N] which of the SS_TABLE_RING sampling-table versions each env draws from (ss_set_sample_cdf) */
 } ss_state_view;
 
 typedef struct ss_env ss_env;
@@ -100,9 +103,17 @@ void ss_host_free(void* p);
 /* update_curriculum / update_specialist / update_sample_prob -- walker3d_envs.py:1346-1356, :604-622,
  * :1317-1320 (mike.py:856-866, :827-830) through envs_utils.py:568-586.  The caller passes the
  * normalised cumulative table exactly as RandomState.choice builds it (cdf = cumsum(p/p.sum());
- * cdf /= cdf[-1]); n_cells must be 11^5.  One table shared by all envs (train.py:269-271 broadcasts
- * one table).  apply_now != 0 reproduces update_sample_prob's immediate re-sample of the next-next
- * stone for envs whose update_terrain flag is set. */
+ * cdf /= cdf[-1]); n_cells must be 11^5.  Every call installs a new table VERSION (a ring of SS_TABLE_RING versions
+ * lives on the device, each env holds the index of the one it draws from):
+ *   apply_now == 0  update_curriculum / update_specialist: every env takes the new table (the reference calls the method
+ *                   on every env unconditionally, envs_utils.py:580-586);
+ *   apply_now != 0  update_sample_prob (mike.py:827-830): ONLY the envs whose update_terrain flag is set -- they advanced
+ *                   a stone in their last step -- take it and re-sample their next-next stone at once; every other env
+ *                   keeps drawing from the version it has, exactly like a reference env ignores the table it is sent.
+ * When the ring wraps, envs still on the version being overwritten move to the oldest surviving one (the only deviation:
+ * an env that has not advanced a stone across SS_TABLE_RING consecutive table updates). */
+/* current head of the version ring and how many versions were ever installed (checkpoints) */
+int ss_table_ring_state(const ss_env* env, int32_t* head, int64_t* count);
 int ss_set_sample_cdf(ss_env* env, const double* cdf_host, int32_t n_cells, int32_t apply_now, void* stream);
 
 /* set_env_params / set_robot_params -- env_base.py:73-85 through envs_utils.py:560-566: the reference setattr()s

@@ -15,7 +15,7 @@ NQ, ND, NJ, OBS, NWARM, NSCAL, NINT, MTW = 28, 27, 21, 60, 16, 16, 8, 625
 
 
 class StateView(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt")]
+    _fields_ = [(n, ctypes.c_void_p) for n in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt", "table_slot")]
 
 
 def build(force=False):
@@ -34,7 +34,7 @@ def alloc_state(n, n_steps, rendered):
         q=np.zeros((n, NQ)), qd=np.zeros((n, ND)), warm=np.zeros((n, NWARM)),
         terrain=np.zeros((n, n_steps, 6)), plank=np.zeros((n, rendered, 6)),
         scalars=np.zeros((n, NSCAL)), ints=np.zeros((n, NINT), np.int32),
-        mt=np.zeros((n, 2, MTW), np.uint32))
+        mt=np.zeros((n, 2, MTW), np.uint32), table_slot=np.zeros(n, np.int32))
 
 
 def make_view(state):

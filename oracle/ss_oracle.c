@@ -173,6 +173,7 @@ typedef struct {
     int next_step, reached_count, mirrored, elapsed, ep_len, update_terrain, phantom_idx, started;
     mt_t rng, grng;
     double trace_q[4][SS_NQ], trace_qd[4][ND];
+    int tslot;                                     /* sampling-table version this env draws from */
     int32_t ev_cur[SS_NEV], trace_ev[4][SS_NEV];   /* discrete decisions of each substep: limit rows (lo / hi hinge masks), contact ids */
     /* scratch shared between calc_* functions of one step */
     double body_rpy[3], joint_speeds[NJ], joint_angles[NJ], robot_state[50];
@@ -182,7 +183,8 @@ typedef struct {
 } env_t;
 
 struct sso_env {
-    ss_model M; ss_params P; int n; env_t* e; double* cdf; int n_cells;
+    ss_model M; ss_params P; int n; env_t* e; double* cdf; int n_cells;      /* cdf: ring of SS_TABLE_RING versions */
+    int table_head; long table_count;
 };
 
 static int g_threads = 0;
@@ -832,7 +834,8 @@ static void sample_next_next_step(const struct sso_env* S, env_t* e) {
     const ss_params* P = &S->P;
     double u = mt_double(&e->rng);
     int lo = 0, hi = S->n_cells;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < S->cdf[mid]) hi = mid; else lo = mid + 1; }
+    const double* cdf = S->cdf + (size_t)e->tslot * S->n_cells;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < cdf[mid]) hi = mid; else lo = mid + 1; }
     int idx = lo < S->n_cells ? lo : S->n_cells - 1, g = SS_GRID;
     int i4 = idx % g, i3 = (idx / g) % g, i2 = (idx / (g * g)) % g, i1 = (idx / (g * g * g)) % g, i0 = idx / (g * g * g * g);
     set_next_next_step_location(P, e, P->pitch_samples[i1] + M_PI / 2, P->yaw_samples[i0], P->r_samples[i2],
@@ -1006,7 +1009,8 @@ int sso_create(const ss_model* model, const ss_params* params, int32_t n, const 
     S->M = *model; S->P = *params; S->n = n;
     S->e = calloc(n, sizeof(env_t));
     S->n_cells = SS_GRID_CELLS;
-    S->cdf = malloc(sizeof(double) * S->n_cells);
+    S->cdf = malloc(sizeof(double) * S->n_cells * SS_TABLE_RING);
+    S->table_head = 0; S->table_count = 1;
     for (int i = 0; i < S->n_cells; i++) S->cdf[i] = (double)(i + 1) / S->n_cells;
     for (int i = 0; i < n; i++) {
         env_t* e = &S->e[i];
@@ -1119,11 +1123,24 @@ int sso_create_temp_states(sso_env* S, int32_t variant, const double* grid, cons
     return 0;
 }
 
+/* Every call installs a new table VERSION in a ring of SS_TABLE_RING.  apply_now == 0 (update_curriculum /
+ * update_specialist, called on every env: envs_utils.py:580-586): all envs take it.  apply_now != 0 (update_sample_prob,
+ * walker3d_envs.py:1317-1320 / mike.py:827-830): `if self.update_terrain: self.yaw_pitch_r_tilt_prob = ...;
+ * self.update_terrain_info()` -- only the envs that advanced a stone in their last step take the table and re-sample; the
+ * others keep the one they have.  When the ring wraps, envs still on the version being overwritten move to the oldest
+ * surviving one. */
 int sso_set_sample_cdf(sso_env* S, const double* cdf, int32_t n_cells, int32_t apply_now) {
     if (n_cells != SS_GRID_CELLS) return SS_ERR_ARG;
-    memcpy(S->cdf, cdf, sizeof(double) * n_cells);
-    if (apply_now)                                        /* update_sample_prob walker3d_envs.py:1317-1320 */
-        for (int i = 0; i < S->n; i++) if (S->e[i].update_terrain) update_terrain_info(S, &S->e[i]);
+    const int slot = (S->table_head + 1) % SS_TABLE_RING;
+    if (S->table_count >= SS_TABLE_RING)
+        for (int i = 0; i < S->n; i++) if (S->e[i].tslot == slot) S->e[i].tslot = (slot + 1) % SS_TABLE_RING;
+    memcpy(S->cdf + (size_t)slot * n_cells, cdf, sizeof(double) * n_cells);
+    S->table_head = slot; S->table_count++;
+    for (int i = 0; i < S->n; i++) {
+        env_t* e = &S->e[i];
+        if (!apply_now) e->tslot = slot;
+        else if (e->update_terrain) { e->tslot = slot; update_terrain_info(S, e); }
+    }
     return 0;
 }
 
@@ -1154,9 +1171,12 @@ int sso_get_state(sso_env* S, ss_state_view* v) {
             memcpy(m, e->rng.mt, 624 * 4); m[624] = e->rng.pos;
             memcpy(m + SS_MT_WORDS, e->grng.mt, 624 * 4); m[SS_MT_WORDS + 624] = e->grng.pos;
         }
+        if (v->table_slot) v->table_slot[i] = e->tslot;
     }
     return 0;
 }
+
+int sso_table_ring_state(const sso_env* S, int32_t* head, int64_t* count) { *head = S->table_head; *count = S->table_count; return 0; }
 
 int sso_set_state(sso_env* S, const ss_state_view* v) {
     int ns = S->P.n_steps, nr = S->P.rendered;
@@ -1185,6 +1205,7 @@ int sso_set_state(sso_env* S, const ss_state_view* v) {
             memcpy(e->rng.mt, m, 624 * 4); e->rng.pos = m[624];
             memcpy(e->grng.mt, m + SS_MT_WORDS, 624 * 4); e->grng.pos = m[SS_MT_WORDS + 624];
         }
+        if (v->table_slot) e->tslot = v->table_slot[i] >= 0 && v->table_slot[i] < SS_TABLE_RING ? v->table_slot[i] : 0;
     }
     return 0;
 }

@@ -69,7 +69,8 @@ struct DevState {
     double* scal;       // [N][SS_NSCAL]
     int* ints;          // [N][SS_NINT]
     uint32_t* mt;       // [N][2][SS_MT_WORDS]
-    const double* cdf;  // [n_cells]
+    const double* cdf;  // [SS_TABLE_RING][n_cells] sampling-table versions
+    int* tslot;         // [N] the version each env draws from
     int n_cells;
     double* trace_q;    // [4][N][28] or null
     double* trace_qd;   // [4][N][27] or null

@@ -325,7 +325,8 @@ __device__ __forceinline__ void sample_next_next_step(const DevModel& M, const D
     uint32_t* mt = S.mt + (size_t)e * 2 * SS_MT_WORDS;
     double u = mt_one_double_warp(mt, E.mtpos, W.u.d, lane);
     int lo = 0, hi = S.n_cells;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < S.cdf[mid]) hi = mid; else lo = mid + 1; }
+    const double* cdf = S.cdf + (size_t)S.tslot[e] * S.n_cells;      // this env's table version (ss_set_sample_cdf)
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (u < cdf[mid]) hi = mid; else lo = mid + 1; }
     int idx = lo < S.n_cells ? lo : S.n_cells - 1;
     const int g = SS_GRID;
     int i4 = idx % g, i3 = (idx / g) % g, i2 = (idx / (g * g)) % g, i1 = (idx / (g * g * g)) % g, i0 = idx / (g * g * g * g);
@@ -698,14 +699,16 @@ __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const DevModel* gm, co
 }
 
 // update_sample_prob's immediate re-sample (walker3d_envs.py:1317-1320): envs whose update_terrain flag is set
-__global__ void __launch_bounds__(BLOCK) resample_kernel(const DevModel* gm, DevState S) {
+__global__ void __launch_bounds__(BLOCK) resample_kernel(const DevModel* gm, DevState S, int slot) {
     BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
     stage_model(B, gm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
     if (e >= S.n) return;
     Env E; env_load(S, e, lane, E);
-    if (E.update_terrain) {
+    if (E.update_terrain) {                  // mike.py:827-830: only an env that advanced a stone takes the table it is sent
+        if (lane == 0) S.tslot[e] = slot;
+        __syncwarp();
         float rpy[3]; quat_to_rpy(E.quat, rpy);
         update_terrain_info(B.M, S, B.W[warp], e, E, rpy[2], lane);
         env_store(S, e, lane, E);
@@ -813,6 +816,13 @@ __global__ void __launch_bounds__(TS_CELLS) temp_fill_kernel(const DevModel* gm,
         else val = make_float4(cellv[cell][1], cellv[cell][2], cellv[cell][3], cellv[cell][4]);
         __stcs(o4 + v, val);
     }
+}
+
+// sampling-table versions: from < 0: every env takes version `to` (update_curriculum / update_specialist); else the envs on
+// version `from` move to `to` (the ring is about to overwrite `from`)
+__global__ void table_assign_kernel(int* __restrict__ tslot, int n, int from, int to) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n && (from < 0 || tslot[e] == from)) tslot[e] = to;
 }
 
 // Order the envs of [e_begin, e_end) by the number of contacts they carried in their last substep (the warm-start list),
@@ -935,6 +945,7 @@ struct ss_env {
     DevModel* dm = nullptr;
     DevState S{};
     double* cdf = nullptr;
+    int table_head = 0; int64_t table_count = 1;     // ring of SS_TABLE_RING sampling-table versions (slot 0: the uniform table)
     int64_t launches = 0;
     size_t smem = 0;
     bool trace = false, debug = false;
@@ -1078,8 +1089,9 @@ static int create_device_state(ss_env* E, const ss_model* model, const uint32_t*
     CK(cudaMalloc(&S.err, sizeof(int))); CK(cudaMemset(S.err, 0, sizeof(int)));
     CK(cudaMalloc(&E->sort_keys, N)); CK(cudaMalloc(&E->sort_bins, SORT_SLOT * sizeof(int)));
     { std::vector<int> id(N); for (size_t i = 0; i < N; i++) id[i] = (int)i; CK(cudaMemcpy(S.perm, id.data(), N * sizeof(int), cudaMemcpyHostToDevice)); }
-    CK(cudaMalloc(&E->cdf, (size_t)SS_GRID_CELLS * sizeof(double)));
+    CK(cudaMalloc(&E->cdf, (size_t)SS_TABLE_RING * SS_GRID_CELLS * sizeof(double)));
     S.cdf = E->cdf;
+    CK(cudaMalloc(&S.tslot, N * sizeof(int))); CK(cudaMemset(S.tslot, 0, N * sizeof(int)));
     CK(cudaMemset(S.sv, 0, N * 64 * sizeof(float)));
     {
         std::vector<float> w(N * SS_NWARM, 0.f);
@@ -1124,7 +1136,7 @@ void ss_destroy(ss_env* E) {
     cudaDeviceSynchronize();
     DevState& S = E->S;
     cudaFree(E->dm); cudaFree(S.pos); cudaFree(S.sv); cudaFree(S.warm); cudaFree(S.terrain); cudaFree(S.plank);
-    cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(S.perm); cudaFree(S.err); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.trace_ev); cudaFree(S.dbg);
+    cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(S.perm); cudaFree(S.err); cudaFree(S.tslot); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.trace_ev); cudaFree(S.dbg);
     cudaFreeHost(E->h_act); cudaFreeHost(E->h_rec); cudaFreeHost(E->h_obs); cudaFree(E->d_act);
     cudaFree(E->ts_base); cudaFree(E->ts_ctx); cudaFree(E->sort_keys); cudaFree(E->sort_bins);
     if (E->own) cudaStreamDestroy(E->own);
@@ -1286,14 +1298,26 @@ int ss_set_sample_cdf(ss_env* E, const double* cdf, int32_t n_cells, int32_t app
     // The table comes from pageable host memory.  A plain cudaMemcpy returns once the data is STAGED; the DMA itself is
     // ordered in the legacy default stream only, which cudaStreamNonBlocking streams do not wait for -- the re-sample
     // below (or the next ss_step_host) could read a half-written table.  Copy on the stream that uses it and wait.
-    CK(cudaMemcpyAsync(E->cdf, cdf, (size_t)n_cells * 8, cudaMemcpyHostToDevice, st));
+    // a new table VERSION (include/ss_env.h): envs still on the ring slot about to be overwritten move to the oldest survivor
+    const int slot = (E->table_head + 1) % SS_TABLE_RING, nb = (E->n + 255) / 256;
+    if (E->table_count >= SS_TABLE_RING) table_assign_kernel<<<nb, 256, 0, st>>>(E->S.tslot, E->n, slot, (slot + 1) % SS_TABLE_RING);
+    CK(cudaMemcpyAsync(E->cdf + (size_t)slot * n_cells, cdf, (size_t)n_cells * 8, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
-    if (apply_now) {
-        resample_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S);
+    E->table_head = slot; E->table_count++;
+    if (apply_now) {                          // update_sample_prob: flagged envs take the version and re-sample at once
+        resample_kernel<<<grid_for(E->n), BLOCK, E->smem, st>>>(E->dm, E->S, slot);
         E->launches++;
-        CK(cudaGetLastError());
-        if (!stream) CK(cudaStreamSynchronize(st));
+    } else {                                  // update_curriculum / update_specialist: every env takes it
+        table_assign_kernel<<<nb, 256, 0, st>>>(E->S.tslot, E->n, -1, slot);
     }
+    CK(cudaGetLastError());
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return SS_OK;
+}
+
+int ss_table_ring_state(const ss_env* E, int32_t* head, int64_t* count) {
+    if (!E || !head || !count) return fail(SS_ERR_ARG, "ss_table_ring_state: bad argument");
+    *head = E->table_head; *count = E->table_count;
     return SS_OK;
 }
 
@@ -1365,6 +1389,7 @@ int ss_get_state(ss_env* E, ss_state_view* v) {
     if (v->scalars) CK(cudaMemcpy(v->scalars, S.scal, N * SS_NSCAL * 8, cudaMemcpyDeviceToHost));
     if (v->ints) CK(cudaMemcpy(v->ints, S.ints, N * SS_NINT * 4, cudaMemcpyDeviceToHost));
     if (v->mt) CK(cudaMemcpy(v->mt, S.mt, N * 2 * SS_MT_WORDS * 4, cudaMemcpyDeviceToHost));
+    if (v->table_slot) CK(cudaMemcpy(v->table_slot, S.tslot, N * 4, cudaMemcpyDeviceToHost));
     return SS_OK;
 }
 
@@ -1398,6 +1423,10 @@ int ss_set_state(ss_env* E, const ss_state_view* v) {
     if (v->scalars) CK(cudaMemcpy(S.scal, v->scalars, N * SS_NSCAL * 8, cudaMemcpyHostToDevice));
     if (v->ints) CK(cudaMemcpy(S.ints, v->ints, N * SS_NINT * 4, cudaMemcpyHostToDevice));
     if (v->mt) CK(cudaMemcpy(S.mt, v->mt, N * 2 * SS_MT_WORDS * 4, cudaMemcpyHostToDevice));
+    if (v->table_slot) {
+        for (size_t i = 0; i < N; i++) if (v->table_slot[i] < 0 || v->table_slot[i] >= SS_TABLE_RING) return fail(SS_ERR_ARG, "ss_set_state: table_slot out of range");
+        CK(cudaMemcpy(S.tslot, v->table_slot, N * 4, cudaMemcpyHostToDevice));
+    }
     // copies from pageable memory return once staged; their DMAs are ordered in the legacy default stream only, which the
     // library's cudaStreamNonBlocking streams (ss_step_host) do not wait for: make "synchronous" true for every stream
     CK(cudaDeviceSynchronize());

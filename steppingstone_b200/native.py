@@ -21,6 +21,7 @@ INCLUDE = os.path.join(REPO_DIR, "include")
 
 NQ, ND, NJ, OBS, NWARM, NSCAL, NINT, MTW, GRID_CELLS = 28, 27, 21, 60, 16, 16, 8, 625, 11 ** 5
 NEV = 18         # int32 per env and substep in ss_substep_events
+TABLE_RING = 8   # sampling-table versions kept alive on the device (SS_TABLE_RING)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -28,7 +29,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 class StateView(ctypes.Structure):
     """``ss_state_view`` (include/ss_env.h)."""
-    _fields_ = [(n, ctypes.c_void_p) for n in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt")]
+    _fields_ = [(n, ctypes.c_void_p) for n in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt", "table_slot")]
 
 
 def _sources():
@@ -93,6 +94,7 @@ _SIGNATURES = {
     "ss_host_alloc": (ctypes.c_int, [ctypes.c_size_t, _P]),
     "ss_host_free": (None, [_P]),
     "ss_set_sample_cdf": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
+    "ss_table_ring_state": (ctypes.c_int, [_P, _P, _P]),
     "ss_update_tables": (ctypes.c_int, [_P, _P, _P, _P]),
     "ss_temp_state_cells": (ctypes.c_int64, [_I32]),
     "ss_create_temp_states": (ctypes.c_int, [_P, _I32, _P, _P, _P, _P]),
@@ -154,7 +156,7 @@ def alloc_state(n, n_steps, rendered):
         q=np.zeros((n, NQ)), qd=np.zeros((n, ND)), warm=np.zeros((n, NWARM)),
         terrain=np.zeros((n, n_steps, 6)), plank=np.zeros((n, rendered, 6)),
         scalars=np.zeros((n, NSCAL)), ints=np.zeros((n, NINT), np.int32),
-        mt=np.zeros((n, 2, MTW), np.uint32))
+        mt=np.zeros((n, 2, MTW), np.uint32), table_slot=np.zeros(n, np.int32))
 
 
 def make_view(state):

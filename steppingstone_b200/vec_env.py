@@ -215,6 +215,7 @@ class BatchedStepperEnv:
         self._no_infos = (_NO_INFO,) * self.num_envs
         self.curriculum = 0
         self._table = None                                                  # uniform until a table is set
+        self._table_log = []                                                # the table versions set so far, oldest first (<= TABLE_RING)
         N = self.num_envs
         if log_dir and output == "torch":
             raise NotImplementedError("log_dir (Monitor csv files) needs output='numpy': device mode keeps the episode "
@@ -305,6 +306,8 @@ class BatchedStepperEnv:
     # ------------------------------------------------------------------ curriculum ops (envs_utils.py:560-590)
     def _set_table(self, p, apply_now=False):
         self._table = np.array(p, dtype=np.float64).reshape(-1)             # kept for save_state
+        self._table_log.append(self._table)                                  # the device keeps a ring of the last TABLE_RING versions
+        del self._table_log[:-native.TABLE_RING]
         cdf = seeding.choice_cdf(p)
         stream = self._stream() if self.output == "torch" else None
         native.check(self._lib.ss_set_sample_cdf(self._h, cdf.ctypes.data, cdf.size, int(apply_now), stream), "ss_set_sample_cdf")
@@ -326,10 +329,10 @@ class BatchedStepperEnv:
         (``update_sample_prob_1/_2``, walker3d_envs.py:1307-1315): those are embedded at index 0 of the missing axes --
         every r / tilt sample of the stepper envs is the same value (mike.py:74-76), so this is the draw they mean.
 
-        Difference from the reference: there each env keeps its own table and takes a new one ONLY if it advanced a stone
-        in its last step (``if self.update_terrain:``, mike.py:828) -- envs that did not keep sampling from their old
-        table.  Here the one shared table is replaced for every env; the immediate re-sample of the next-next stone
-        happens, as in the reference, only for the envs whose ``update_terrain`` flag is set."""
+        As in the reference (``if self.update_terrain:``, mike.py:828), ONLY the envs that advanced a stone in their last step
+        take the table and re-sample their next-next stone at once; every other env keeps drawing from the table it has.
+        The device holds a ring of the last 8 table versions and a version index per env (include/ss_env.h); an env that
+        has not advanced a stone across 8 consecutive updates is moved to the oldest surviving version."""
         p = expand_sample_table(probs, self.num_envs)
         self._set_table(p, apply_now=True)
 
@@ -439,7 +442,7 @@ class BatchedStepperEnv:
         return {"q": (np.float64, (N, native.NQ)), "qd": (np.float64, (N, native.ND)), "warm": (np.float64, (N, native.NWARM)),
                 "terrain": (np.float64, (N, self.n_steps, 6)), "plank": (np.float64, (N, self.rendered, 6)),
                 "scalars": (np.float64, (N, native.NSCAL)), "ints": (np.int32, (N, native.NINT)),
-                "mt": (np.uint32, (N, 2, native.MTW))}
+                "mt": (np.uint32, (N, 2, native.MTW)), "table_slot": (np.int32, (N,))}
 
     def set_state(self, st):
         """Any subset of the ``get_state`` arrays.  Every array is converted to the dtype the C-ABI copies (a float32 ``q``
@@ -472,9 +475,13 @@ class BatchedStepperEnv:
         rollout bit for bit.  The reference has no equivalent (its env state dies with the worker processes)."""
         import json
         st = self.get_state()
+        head, count = ctypes.c_int32(0), ctypes.c_int64(0)
+        native.check(self._lib.ss_table_ring_state(self._h, ctypes.byref(head), ctypes.byref(count)), "ss_table_ring_state")
         np.savez_compressed(self._npz(path), env_id=self.env_id, seed=self.seed, first_env=self.first_env,
                             n_steps=self.n_steps, rendered=self.rendered, curriculum=self.curriculum,
                             has_table=self._table is not None, table=(self._table if self._table is not None else np.zeros(0)),
+                            table_log=(np.stack(self._table_log) if self._table_log else np.zeros((0, native.GRID_CELLS))),
+                            table_head=head.value, table_count=count.value,
                             overrides=json.dumps(self._overrides), terrain_mode=json.dumps(self._terrain_mode),
                             power=self._power, tau_max=self._tables["tau_max"], pd_p=self._tables["pd_p"],
                             pd_d=self._tables["pd_d"], fake_grid=self._fake_grid, **st)
@@ -497,15 +504,34 @@ class BatchedStepperEnv:
                 self._fake_grid = np.array(z["fake_grid"])
                 self._push_tables()
                 self._max_episode_steps = self._params.max_episode_steps
-                if bool(z["has_table"]):
-                    self._set_table(np.array(z["table"]))
-                elif self._table is not None:                              # back to the table ss_create installs: uniform
-                    cdf = (np.arange(native.GRID_CELLS, dtype=np.float64) + 1.0) / native.GRID_CELLS
-                    stream = self._stream() if self.output == "torch" else None
-                    native.check(self._lib.ss_set_sample_cdf(self._h, cdf.ctypes.data, cdf.size, 0, stream), "ss_set_sample_cdf")
-                    self._table = None
                 self.curriculum = int(z["curriculum"])
-            self.set_state({k: z[k] for k in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt")})
+            slots = None
+            if "table_log" in z.files:
+                # The sampling-table versions the envs draw from (a ring on the device, a version index per env): re-install
+                # the versions that were alive, oldest first -- the uniform table of ss_create too while it was still in the
+                # ring -- then point every env at the version of the same AGE it had.
+                K = native.TABLE_RING
+                log = [np.array(t) for t in z["table_log"]]
+                head_s, count_s = int(z["table_head"]), int(z["table_count"])
+                stream = self._stream() if self.output == "torch" else None
+                if count_s <= K and (log or self._table_log):
+                    cdf = (np.arange(native.GRID_CELLS, dtype=np.float64) + 1.0) / native.GRID_CELLS
+                    native.check(self._lib.ss_set_sample_cdf(self._h, cdf.ctypes.data, cdf.size, 0, stream), "ss_set_sample_cdf")
+                self._table_log = []
+                for t in log:
+                    self._set_table(t)
+                if not log:
+                    self._table = None
+                head, count = ctypes.c_int32(0), ctypes.c_int64(0)
+                native.check(self._lib.ss_table_ring_state(self._h, ctypes.byref(head), ctypes.byref(count)), "ss_table_ring_state")
+                age = (head_s - np.array(z["table_slot"], dtype=np.int64)) % K
+                slots = ((head.value - age) % K).astype(np.int32)
+            elif "overrides" in z.files and bool(z["has_table"]):
+                self._set_table(np.array(z["table"]))
+            state = {k: z[k] for k in ("q", "qd", "warm", "terrain", "plank", "scalars", "ints", "mt")}
+            if slots is not None:
+                state["table_slot"] = slots
+            self.set_state(state)
 
     def enable_substep_trace(self, on=True):
         native.check(self._lib.ss_enable_substep_trace(self._h, int(on)), "ss_enable_substep_trace")

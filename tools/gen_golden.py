@@ -124,7 +124,7 @@ class RefWorker:
 
 
 def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=None, curriculum=None, oracle_params=None,
-           temp_states=False, sample_prob_every=0, sample_prob_at_done=False):
+           temp_states=False, sample_prob_every=0, sample_prob_at_done=False, sample_prob_unflagged_every=0):
     """tape_fn(t, worker, sim) -> (q, qd, contact) for step t.  temp_states: after every step that advanced a stone
     call the reference's create_temp_states_1 / _2 / create_temp_states (value-guided sampling probes) and record them."""
     fk = make_oracle(kind, seed)
@@ -144,12 +144,15 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
         EPR.append(info["episode"]["r"] if "episode" in info else 0.0)
         EPL.append(info["episode"]["l"] if "episode" in info else 0)
         NXT.append(nxt); CNT.append(cnt); POT.append(pot)
-        if sample_prob_every and (not d or sample_prob_at_done) and w.env.update_terrain and (d or (nxt % sample_prob_every) != 0):
+        unflagged = bool(sample_prob_unflagged_every) and not w.env.update_terrain and t % sample_prob_unflagged_every == 3
+        if unflagged or (sample_prob_every and (not d or sample_prob_at_done) and w.env.update_terrain and (d or (nxt % sample_prob_every) != 0)):
             # update_sample_prob (mike.py:827-830 through envs_utils.py:568-571) right after a step that advanced a stone
             # (the only moment the reference env takes the table): new sampling table + immediate re-sample of the
             # next-next stone.  Skipped on every third stone so that draws from a table set earlier are covered too.
             # sample_prob_at_done: also after an episode that ENDED on an advance step -- reset() does not clear
             # update_terrain, so the freshly reset env takes the table and re-samples its stone 2 (tape G).
+            # sample_prob_unflagged_every: the table is ALSO sent at steps that advanced nothing -- the reference env
+            # ignores it then (`if self.update_terrain:`, mike.py:828) and keeps drawing from the table it has (tape G).
             table = sp_rng.rand(11, 11, 11, 11, 11) * (sp_rng.rand(11, 11, 11, 11, 11) < 0.02)
             table[5, 5, 0, 5, 5] += 1e-3
             table = table.astype(np.float32).astype(np.float64)          # stored as float32 in the fixture: keep it exact
@@ -184,6 +187,8 @@ def record(name, kind, seed, actions, tape_fn, T, time_limit=1000, env_params=No
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     print("%-28s T=%d episodes=%d max next_step=%d reward[min,max]=[%.2f, %.2f] sample_prob calls %d (%d right after a done step)" % (
         name, T, int(np.sum(DONE)), int(np.max(NXT)), np.min(REW), np.max(REW), len(sp_step), sum(bool(DONE[t]) for t in sp_step)))
+    if sample_prob_unflagged_every:
+        print("   ... %d of them at steps that advanced no stone (the env must ignore the table)" % sum(1 for t in sp_step if t % sample_prob_unflagged_every == 3))
 
 
 def simulated_tape(kind, seed, actions, T, curriculum=None):
@@ -264,7 +269,8 @@ def main():
         rng = np.random.RandomState(67)
         acts = np.clip(rng.randn(T, 21) * 0.3, -1.2, 1.2).astype(np.float32)
         record("mike_ghost_sampleprob_at_done", 1, 15, acts, ghost_tape(1, 15, rng, 6), T, time_limit=23,
-               env_params={"stop_frames": 5}, curriculum=5, sample_prob_every=3, sample_prob_at_done=True)
+               env_params={"stop_frames": 5}, curriculum=5, sample_prob_every=3, sample_prob_at_done=True,
+               sample_prob_unflagged_every=7)
         if only:
             return
     for kind, nm in ((0, "w3d"), (1, "mike")):

@@ -143,3 +143,27 @@ def test_non_finite_action_on_the_device_path_is_flagged():
     with pytest.raises(AssertionError):
         a_env.check_errors()
     a_env.check_errors()                       # the flag was cleared by the failing check
+
+
+@pytest.mark.gpu
+def test_mirror_and_minibatching_on_the_device():
+    """SURVEY 8f.2 on CUDA tensors: the mirror function (common/envs_utils.py:687-740 restated as one gather + sign) gives
+    what it gives on the host, is an involution on observations / actions, and ``feed_forward_generator``'s device
+    permutation visits every sample of the rollout exactly once per epoch (storage.py:84-103)."""
+    from steppingstone_b200 import mirror
+    from steppingstone_b200.storage import RolloutStorage
+    dev = torch.device("cuda", 0)
+    f = mirror.get_mirror_function(mirror.get_mirror_indices())
+    g = torch.Generator().manual_seed(1)
+    obs = torch.randn(33, 60, generator=g); act = torch.randn(33, 21, generator=g); z = torch.zeros(33, 1)
+    host = f((obs, z, act, z, z, z, z, z))
+    devo = f(tuple(t.to(dev) for t in (obs, z, act, z, z, z, z, z)))
+    assert all(torch.equal(a, b.cpu()) for a, b in zip(host, devo))
+    m_obs, m_act = devo[0][33:], devo[2][33:]
+    twice = f((m_obs, z.to(dev), m_act, z.to(dev), z.to(dev), z.to(dev), z.to(dev), z.to(dev)))
+    assert torch.equal(twice[0][33:].cpu(), obs) and torch.equal(twice[2][33:].cpu(), act)
+    T, N = 7, 50
+    rs = RolloutStorage(T, N, (60,), 21, 1, device=dev)
+    rs.observations[:-1, :, 0] = torch.arange(T * N, device=dev, dtype=torch.float32).view(T, N)      # tag every sample
+    seen = torch.cat([mb[0][:, 0] for mb in rs.feed_forward_generator(torch.zeros(T, N, 1, device=dev), 4)])
+    assert seen.numel() == T * N and torch.equal(seen.sort().values, torch.arange(T * N, device=dev, dtype=torch.float32))

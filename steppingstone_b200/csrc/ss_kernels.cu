@@ -1231,23 +1231,20 @@ int ss_step_host(ss_env* E, const float* act, float* obs, double* rew, uint8_t* 
     const int N = E->n;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    {   // robots.py:290 `assert np.isfinite(a).all()` while copying into the pinned buffer: refused before anything runs
-        // two floats per 64-bit word: x = the exponent bits that are NOT set (zero in a half <=> that float is inf / nan);
-        // (x | bit 31 of each half) - 2^23 per half keeps bit 31 exactly where the exponent field was non-zero
-        const size_t cnt = (size_t)N * NJ, n64 = cnt / 2;
-        const uint64_t EXP = 0x7f8000007f800000ull, TOP = 0x8000000080000000ull, ONE = 0x0080000000800000ull;
-        uint64_t bad = 0;
-        for (size_t i = 0; i < n64; i++) {
-            uint64_t w; memcpy(&w, reinterpret_cast<const char*>(act) + 8 * i, 8);
-            memcpy(reinterpret_cast<char*>(E->h_act) + 8 * i, &w, 8);
-            bad |= ~(((~w & EXP) | TOP) - ONE) & TOP;
-        }
-        if (cnt & 1) { const float last = act[cnt - 1]; E->h_act[cnt - 1] = last; if (!std::isfinite(last)) bad = 1; }
-        if (bad) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
+    // robots.py:290 `assert np.isfinite(a).all()`: checked on the pinned copy BEFORE anything is enqueued (a refused batch
+    // leaves the envs untouched).  (u & exponent mask) + 2^23 carries into bit 31 exactly when the exponent field is all
+    // ones (inf / nan): one and + add + or per float, vectorised by the host compiler.
+    const size_t cnt = (size_t)N * NJ;
+    memcpy(E->h_act, act, cnt * 4);
+    {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(E->h_act);
+        uint32_t bad = 0;
+        for (size_t i = 0; i < cnt; i++) bad |= (p[i] & 0x7f800000u) + 0x00800000u;
+        if (bad & 0x80000000u) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
     }
     const double t1 = now();
     bool direct; float* ot = obs_target(E, obs, &direct);
-    CK(cudaMemcpyAsync(E->d_act, E->h_act, (size_t)N * NJ * 4, cudaMemcpyHostToDevice, E->own));
+    CK(cudaMemcpyAsync(E->d_act, E->h_act, cnt * 4, cudaMemcpyHostToDevice, E->own));
     rc = launch_step(E, E->d_act, ot, nullptr, nullptr, nullptr, nullptr, nullptr, E->own, 1, 0, N, E->h_rec); if (rc) return rc;
     const double t2 = now();
     CK(cudaStreamSynchronize(E->own));

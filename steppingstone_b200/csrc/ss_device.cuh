@@ -491,6 +491,12 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
 #else
     ldl_steps<0>(Hr, myDinv, lane);
 #endif
+#if SS_SPARSE_LDL
+    // rows go to shared memory with the scratch part (columns <= lane) zeroed: the U^T solves below then need no
+    // `lane > k` predicate and unroll to SHFL + LDS + FFMA per column
+#pragma unroll
+    for (int j = 0; j < ND; j++) if (j <= lane) Hr[j] = 0.f;
+#endif
     if (lane < ND) {
         float4* row = reinterpret_cast<float4*>(H + lane * HS);
 #pragma unroll
@@ -505,8 +511,8 @@ __device__ __forceinline__ float dynamics_warp(const DevModel& M, WS& W, const f
 #pragma unroll
     for (int k = ND - 1; k >= 1; k--) { float yk = shfl(y, k); if (lane < k) y -= Hr[k] * yk; }
     y *= myDinv;
-#pragma unroll 1
-    for (int k = 0; k < ND - 1; k++) { float xk = shfl(y, k); if (lane > k && lane < ND) y -= H[k * HS + lane] * xk; }
+#pragma unroll
+    for (int k = 0; k < ND - 1; k++) { const float xk = shfl(y, k); y = fmaf(-H[k * HS + lane], xk, y); }     // (lanes >= ND: discarded below)
 #else
 #pragma unroll
     for (int k = 0; k < ND - 1; k++) { float yk = shfl(y, k); if (lane > k && lane < ND) y -= Hr[k] * yk; }
@@ -549,8 +555,8 @@ __device__ __forceinline__ void sparse_usolve(const float* U, float (&z)[HS]) {
 __device__ __forceinline__ float solve_lt(const WarpSmem& W, float u, int lane) {
     const float* H = W.u.s.H;
 #if SS_SPARSE_LDL
-#pragma unroll 1
-    for (int k = 0; k < ND - 1; k++) { float xk = shfl(u, k); if (lane > k && lane < ND) u -= H[k * HS + lane] * xk; }   // U^T x = u
+#pragma unroll
+    for (int k = 0; k < ND - 1; k++) { const float xk = shfl(u, k); u = fmaf(-H[k * HS + lane], xk, u); }   // U^T x = u (scratch columns are zero)
 #else
 #pragma unroll 1
     for (int k = ND - 1; k >= 1; k--) { float xk = shfl(u, k); if (lane < k) u -= H[k * HS + lane] * xk; }

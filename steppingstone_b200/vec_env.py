@@ -139,13 +139,15 @@ class _ArrayPool:
         self.factory = factory or (lambda: np.empty(shape, dtype))
 
     def get(self):
-        for a in self.items:
-            if sys.getrefcount(a) == 3:           # the list's reference, the loop variable, getrefcount's argument
-                return a
+        """-> (array, its data pointer): ``ndarray.ctypes.data`` builds a ctypes object on every access (~1 us each)."""
+        for a, ptr in self.items:
+            if sys.getrefcount(a) == 3:           # the tuple's reference, the loop variable, getrefcount's argument
+                return a, ptr
         a = self.factory()
+        ptr = a.ctypes.data
         if len(self.items) < self.depth:
-            self.items.append(a)
-        return a
+            self.items.append((a, ptr))
+        return a, ptr
 
 
 class _PinnedBlock:
@@ -225,6 +227,7 @@ class BatchedStepperEnv:
             self._timeout = np.zeros(N, np.uint8)
             self._ep_ret = np.zeros(N, np.float32)
             self._ep_len = np.zeros(N, np.int32)
+            self._stat_ptrs = (self._timeout.ctypes.data, self._ep_ret.ctypes.data, self._ep_len.ctypes.data)
             self._pool_obs = _ArrayPool((N, OBS_DIM), np.float32, factory=lambda: _pinned_array(self._lib, (N, OBS_DIM), np.float32))
             self._pool_rew = _ArrayPool((N,), np.float64)
             self._pool_done = _ArrayPool((N,), np.bool_)
@@ -247,8 +250,8 @@ class BatchedStepperEnv:
     def reset(self):
         """ShmemVecEnv.reset (envs_utils.py:542-548)."""
         if self.output == "numpy":
-            obs = self._pool_obs.get()
-            native.check(self._lib.ss_reset_host(self._h, obs.ctypes.data), "ss_reset_host")
+            obs, p_obs = self._pool_obs.get()
+            native.check(self._lib.ss_reset_host(self._h, p_obs), "ss_reset_host")
             return obs
         native.check(self._lib.ss_reset_all(self._h, self._obs.data_ptr(), self._stream()), "ss_reset_all")
         return self._obs
@@ -265,9 +268,8 @@ class BatchedStepperEnv:
             N = self.num_envs
             # arrays nobody else refers to: fresh ones as far as the caller can tell (ShmemVecEnv._decode_obses / step_wait
             # return new arrays every step, envs_utils.py:556-558, 608-620)
-            obs = self._pool_obs.get(); rew = self._pool_rew.get(); dones = self._pool_done.get()
-            rc = self._lib.ss_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, dones.ctypes.data,
-                                        self._timeout.ctypes.data, self._ep_ret.ctypes.data, self._ep_len.ctypes.data)
+            (obs, p_obs), (rew, p_rew), (dones, p_done) = self._pool_obs.get(), self._pool_rew.get(), self._pool_done.get()
+            rc = self._lib.ss_step_host(self._h, a.ctypes.data, p_obs, p_rew, p_done, *self._stat_ptrs)
             if rc != 0:
                 assert np.isfinite(a).all()                                     # robots.py:290
                 native.check(rc, "ss_step_host")

@@ -225,6 +225,6 @@ def test_lazy_infos_behave_like_the_reference_tuple():
     assert bad_masks[:, 0].tolist() == [1, 1, 1, 1, 0, 1] and episode_rewards == [2.0, 1.0]
     assert len(infos) == 6 and infos[-2]["bad_transition"] and infos[0] == {} and len(infos[1:3]) == 2
     pool = _ArrayPool((8,), np.float32)
-    a = pool.get(); ida = id(a); del a
-    b = pool.get(); assert id(b) == ida                         # nobody kept the first array: it is handed out again
-    c = pool.get(); assert c is not b                           # b is still alive in the caller: a fresh array
+    a, pa = pool.get(); ida = id(a); assert pa == a.ctypes.data; del a
+    b, _ = pool.get(); assert id(b) == ida                      # nobody kept the first array: it is handed out again
+    c, _ = pool.get(); assert c is not b                        # b is still alive in the caller: a fresh array

@@ -949,7 +949,7 @@ struct ss_env {
     int64_t launches = 0;
     size_t smem = 0;
     bool trace = false, debug = false;
-    // host-buffer entry points: pinned staging + a pipeline of env slices on separate streams
+    // host-buffer entry points: pinned staging the kernel reads actions from (via one H2D) and writes results into directly
     float *h_act = nullptr, *h_rec = nullptr, *h_obs = nullptr, *d_act = nullptr;     // pinned [N,21], [N,4], [N,60]; device [N,21]
     cudaStream_t own = nullptr;
     double host_t[4] = {};           // last ss_step_host: action copy, enqueue, waiting on the device, unpacking (seconds)

@@ -632,7 +632,9 @@ def expand_sample_table(probs, num_envs):
     if per_env is None:
         raise ValueError("sample_prob must be a [11,11], [11,11,11] or [11,11,11,11,11] table (or one per env)")
     if not np.allclose(per_env, per_env[:1]):
-        raise NotImplementedError("per-env sampling tables are not supported: one table is shared by all envs")
+        raise NotImplementedError("N DIFFERENT sampling tables in one update_sample_prob call are not supported (train.py:266-271 "
+                                  "always sends N copies of one table).  What is per env is which VERSION an env draws from: like in "
+                                  "the reference, only the envs that advanced a stone in their last step take a new table")
     t = per_env[0]
     if t.size == g:
         return t

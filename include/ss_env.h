@@ -87,9 +87,9 @@ int ss_step(ss_env* env, const float* act_dev, float* obs_dev, float* rew_dev, u
 
 /* Same call with HOST buffers (the reference's numpy-in / numpy-out contract, envs_utils.py:550-558, 608-620):
  * rew_host is float64 like the reference's stacked python floats, done_host / timeout_host are 0/1 bytes (numpy
- * bool storage).  One H2D copy of the actions, ONE launch over the batch; the kernel writes the observation rows and a
- * 16-byte scalar record per env straight into pinned host memory -- into obs_host itself when that is pinned
- * (ss_host_alloc / cudaHostAlloc / cudaHostRegister), else into a pinned buffer of the library's that is copied out.
+ * bool storage).  One H2D copy of the actions, ONE launch over the batch; the kernel writes every output straight into
+ * pinned host memory -- into the caller's arrays themselves where they are pinned (ss_host_alloc / cudaHostAlloc /
+ * cudaHostRegister; checked per array), else into a pinned buffer of the library's that is copied out.
  * Returns after everything has landed in the caller's arrays.  A non-finite action fails with SS_ERR_ARG before anything
  * runs (robots.py:290: fatal in the reference too, where the other workers have stepped by then). */
 int ss_step_host(ss_env* env, const float* act_host, float* obs_host, double* rew_host,
@@ -193,7 +193,7 @@ int ss_enable_debug(ss_env* env, int32_t on);
 int ss_debug_read(ss_env* env, float* out_host);
 
 /* host-side breakdown of the last ss_step_host (seconds): out4 = action copy, enqueue, waiting on the
- * device, unpacking result records (bench.py reports it next to e2e) */
+ * device, copying out whatever the caller did not give pinned memory for (bench.py reports it next to e2e) */
 int ss_host_timing(const ss_env* env, double* out4);
 int32_t ss_num_envs(const ss_env* env);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

@@ -30,7 +30,6 @@ namespace ssb {
 #define SS_MINB 1
 #endif
 constexpr int WARPS_PER_BLOCK = SS_WPB;
-constexpr int SS_REC = 4;        // floats per env in the packed scalar record of the host-buffer path: reward, episode return, length, flags
 constexpr int BLOCK = 32 * WARPS_PER_BLOCK;
 
 struct alignas(16) BlockSmem {
@@ -521,11 +520,10 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
                                                          float* __restrict__ obs, float* __restrict__ rew,
                                                          uint8_t* __restrict__ done, uint8_t* __restrict__ timeout,
                                                          float* __restrict__ ep_ret, int32_t* __restrict__ ep_len, int physics,
-                                                         int e_begin, int e_end, float* __restrict__ packed) {
-    // envs [e_begin, e_end) of the batch.  packed != null (host-buffer entry point): `obs` and `packed` are PINNED HOST
-    // memory the kernel writes straight into (zero-copy over PCIe, posted stores) -- the observation row in its final
-    // place, and one 16-byte record per env for the scalars: reward, episode return, episode length (int bits),
-    // done | timeout << 8 | non-finite action << 16 (int bits).
+                                                         int e_begin, int e_end, double* __restrict__ rew64) {
+    // envs [e_begin, e_end) of the batch.  rew64 != null (host-buffer entry point): every output pointer is PINNED HOST
+    // memory the kernel writes straight into (zero-copy over PCIe, posted stores) -- the observation row, and the scalars in
+    // the caller's own types (the reward as float64, like the reference's stacked python floats).
     BlockSmem& B = *reinterpret_cast<BlockSmem*>(smem_raw);
     stage_model_issue(B, gm);                  // the env's state row is fetched while the tables are in flight
     const DevModel& M = B.M;
@@ -641,8 +639,7 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     if (lane >= 6 && lane < ND) {                                                               // unclipped action (q5)
         a_again = act[(size_t)e * NJ + lane - 6];      // re-read (L1/L2 hit): keeps a register free through the physics
     }
-    const bool bad_act = __any_sync(FULL, !isfinite(a_again));
-    if (bad_act) a_again = 0.f;                                        // non-finite action: stepped as zero (see the top)
+    if (__any_sync(FULL, !isfinite(a_again))) a_again = 0.f;           // non-finite action: stepped as zero (see the top)
     m1 = fabsf(a_again * 0.1f * E.v_dof); m2 = a_again * a_again;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) { m1 += __shfl_xor_sync(FULL, m1, off); m2 += __shfl_xor_sync(FULL, m2, off); }
@@ -678,12 +675,8 @@ __global__ void __launch_bounds__(BLOCK, SS_MINB) env_step_kernel(const DevModel
     if (lane == 0) {
         const int to = (d && E.elapsed == M.max_episode_steps) ? 1 : 0;
         const float er = (float)(rint(E.ep_ret * 1e6) / 1e6);
-        if (packed) {
-            *reinterpret_cast<float4*>(packed + (size_t)e * SS_REC) =
-                make_float4(r, er, __int_as_float(E.ep_len), __int_as_float((d ? 1 : 0) | (to << 8) | (bad_act ? 1 << 16 : 0)));
-        } else {
-            rew[e] = r; done[e] = d ? 1 : 0; timeout[e] = to; ep_ret[e] = er; ep_len[e] = E.ep_len;
-        }
+        if (rew64) rew64[e] = (double)r; else rew[e] = r;
+        done[e] = d ? 1 : 0; timeout[e] = to; ep_ret[e] = er; ep_len[e] = E.ep_len;
     }
     env_store(S, e, lane, E);
     if (d) { __syncwarp(); env_reset_from_memory(&M, &S, &W, e, o, lane); }         // envs_utils.py:646-649
@@ -950,7 +943,8 @@ struct ss_env {
     size_t smem = 0;
     bool trace = false, debug = false;
     // host-buffer entry points: pinned staging the kernel reads actions from (via one H2D) and writes results into directly
-    float *h_act = nullptr, *h_rec = nullptr, *h_obs = nullptr, *d_act = nullptr;     // pinned [N,21], [N,4], [N,60]; device [N,21]
+    float *h_act = nullptr, *d_act = nullptr;        // pinned / device [N,21]
+    unsigned char* h_out = nullptr;                  // pinned staging for outputs the caller did not give pinned memory for
     cudaStream_t own = nullptr;
     double host_t[4] = {};           // last ss_step_host: action copy, enqueue, waiting on the device, unpacking (seconds)
     float* ts_base = nullptr; double* ts_ctx = nullptr;      // create_temp_states scratch
@@ -1137,7 +1131,7 @@ void ss_destroy(ss_env* E) {
     DevState& S = E->S;
     cudaFree(E->dm); cudaFree(S.pos); cudaFree(S.sv); cudaFree(S.warm); cudaFree(S.terrain); cudaFree(S.plank);
     cudaFree(S.scal); cudaFree(S.ints); cudaFree(S.mt); cudaFree(S.perm); cudaFree(S.err); cudaFree(S.tslot); cudaFree(E->cdf); cudaFree(S.trace_q); cudaFree(S.trace_qd); cudaFree(S.trace_ev); cudaFree(S.dbg);
-    cudaFreeHost(E->h_act); cudaFreeHost(E->h_rec); cudaFreeHost(E->h_obs); cudaFree(E->d_act);
+    cudaFreeHost(E->h_act); cudaFreeHost(E->h_out); cudaFree(E->d_act);
     cudaFree(E->ts_base); cudaFree(E->ts_ctx); cudaFree(E->sort_keys); cudaFree(E->sort_bins);
     if (E->own) cudaStreamDestroy(E->own);
     delete E;
@@ -1153,7 +1147,7 @@ int ss_reset_all(ss_env* E, float* obs_dev, void* stream) {
 }
 
 static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el,
-                       cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, float* packed = nullptr, int slot = 0) {
+                       cudaStream_t st, int physics, int e_begin = 0, int e_end = -1, double* rew64 = nullptr, int slot = 0) {
     if (e_end < 0) e_end = E->n;
     if (physics == 1 && e_end - e_begin >= 4 * WARPS_PER_BLOCK) {
         int* bins = E->sort_bins; (void)slot;
@@ -1165,10 +1159,10 @@ static int launch_step(ss_env* E, const float* act, float* obs, float* rew, uint
     }
     if (E->S.dbg || E->S.trace_q || E->S.trace_ev)
         env_step_kernel<true><<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
-                                                                                 e_begin, e_end, packed);
+                                                                                 e_begin, e_end, rew64);
     else
         env_step_kernel<false><<<grid_for(e_end - e_begin), BLOCK, E->smem, st>>>(E->dm, E->S, act, obs, rew, done, to, er, el, physics,
-                                                                                  e_begin, e_end, packed);
+                                                                                  e_begin, e_end, rew64);
     E->launches++;
     CK(cudaGetLastError());
     return SS_OK;
@@ -1199,42 +1193,43 @@ int ss_env_post(ss_env* E, const float* act_dev, float* obs_dev, float* rew_dev,
 static int ensure_staging(ss_env* E) {
     if (E->h_act) return SS_OK;
     size_t N = (size_t)E->n;
-    CK(cudaMallocHost(&E->h_act, N * NJ * 4)); CK(cudaMallocHost(&E->h_rec, N * SS_REC * 4)); CK(cudaMallocHost(&E->h_obs, N * SS_OBS * 4));
+    CK(cudaMallocHost(&E->h_act, N * NJ * 4));
+    CK(cudaMallocHost(&E->h_out, N * (SS_OBS * 4 + 8 + 1 + 1 + 4 + 4) + 64));
     CK(cudaMalloc(&E->d_act, N * NJ * 4));
     return SS_OK;
 }
 
-/* Where the kernel writes the observations of a host-buffer call: straight into the caller's array when that is pinned
- * host memory (ss_host_alloc, cudaHostAlloc, cudaHostRegister: device-accessible under unified addressing), else into the
- * library's own pinned buffer, from which the rows are copied afterwards. */
-static float* obs_target(ss_env* E, float* obs, bool* direct) {
+/* Where the kernel writes one output array of a host-buffer call: straight into the caller's array when that is pinned host
+ * memory (ss_host_alloc, cudaHostAlloc, cudaHostRegister: device-accessible under unified addressing), else into the
+ * library's own pinned staging (`stage`), from which it is copied afterwards (*direct = false). */
+static void* out_target(void* user, void* stage, bool* direct) {
     *direct = false;
 #ifndef SS_SIMT_EMU
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, obs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+    if (cudaPointerGetAttributes(&at, user) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
         *direct = true;
-        return static_cast<float*>(at.devicePointer);
+        return at.devicePointer;
     }
     cudaGetLastError();
 #endif
-    return E->h_obs;
+    return stage;
 }
 
-/* Host buffers in, host buffers out.  actions: one copy into pinned memory + one H2D DMA; ONE launch over the whole batch
- * (the sliced pipeline of round 1 paid four partial waves and 24 enqueues per step); the kernel writes observation rows and
- * a 16-byte scalar record per env straight into pinned host memory, so nothing is copied back -- after the stream
- * synchronises the host only widens the scalars into the caller's arrays. */
+/* Host buffers in, host buffers out.  actions: checked while copied into pinned memory, one H2D DMA; ONE launch over the whole
+ * batch (the sliced pipeline of round 1 paid four partial waves and 24 enqueues per step); the kernel writes every output --
+ * observation rows, float64 rewards, done / timeout bytes, episode statistics -- straight into pinned host memory, the
+ * caller's own arrays where those are pinned: nothing is copied back or unpacked. */
 int ss_step_host(ss_env* E, const float* act, float* obs, double* rew, uint8_t* done, uint8_t* to, float* er, int32_t* el) {
     if (!E || !act || !obs || !rew || !done || !to || !er || !el) return fail(SS_ERR_ARG, "ss_step_host: null buffer");
     CK(cudaSetDevice(E->device));
     int rc = ensure_staging(E); if (rc) return rc;
-    const int N = E->n;
+    const size_t N = (size_t)E->n;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     // robots.py:290 `assert np.isfinite(a).all()`: checked on the pinned copy BEFORE anything is enqueued (a refused batch
     // leaves the envs untouched).  (u & exponent mask) + 2^23 carries into bit 31 exactly when the exponent field is all
     // ones (inf / nan): one and + add + or per float, vectorised by the host compiler.
-    const size_t cnt = (size_t)N * NJ;
+    const size_t cnt = N * NJ;
     memcpy(E->h_act, act, cnt * 4);
     {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(E->h_act);
@@ -1243,23 +1238,27 @@ int ss_step_host(ss_env* E, const float* act, float* obs, double* rew, uint8_t* 
         if (bad & 0x80000000u) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");
     }
     const double t1 = now();
-    bool direct; float* ot = obs_target(E, obs, &direct);
+    // staging layout: rew f64 [N] | obs f32 [N,60] | er f32 [N] | el i32 [N] | done u8 [N] | to u8 [N]
+    unsigned char* st = E->h_out;
+    bool d_obs, d_rew, d_done, d_to, d_er, d_el;
+    double* t_rew = (double*)out_target(rew, st, &d_rew);             st += N * 8;
+    float* t_obs = (float*)out_target(obs, st, &d_obs);               st += N * SS_OBS * 4;
+    float* t_er = (float*)out_target(er, st, &d_er);                  st += N * 4;
+    int32_t* t_el = (int32_t*)out_target(el, st, &d_el);              st += N * 4;
+    uint8_t* t_done = (uint8_t*)out_target(done, st, &d_done);        st += N;
+    uint8_t* t_to = (uint8_t*)out_target(to, st, &d_to);
     CK(cudaMemcpyAsync(E->d_act, E->h_act, cnt * 4, cudaMemcpyHostToDevice, E->own));
-    rc = launch_step(E, E->d_act, ot, nullptr, nullptr, nullptr, nullptr, nullptr, E->own, 1, 0, N, E->h_rec); if (rc) return rc;
+    rc = launch_step(E, E->d_act, t_obs, nullptr, t_done, t_to, t_er, t_el, E->own, 1, 0, (int)N, t_rew); if (rc) return rc;
     const double t2 = now();
     CK(cudaStreamSynchronize(E->own));
     const double t3 = now();
-    int32_t any = 0;
-    for (int e = 0; e < N; e++) {
-        const float* r = E->h_rec + (size_t)e * SS_REC;
-        int32_t len, flags; memcpy(&len, r + 2, 4); memcpy(&flags, r + 3, 4);
-        rew[e] = (double)r[0]; er[e] = r[1]; el[e] = len;
-        done[e] = (uint8_t)(flags & 1); to[e] = (uint8_t)((flags >> 8) & 1);
-        any |= flags;
-    }
-    if (!direct) memcpy(obs, E->h_obs, (size_t)N * SS_OBS * 4);
+    if (!d_rew) memcpy(rew, t_rew, N * 8);
+    if (!d_obs) memcpy(obs, t_obs, N * SS_OBS * 4);
+    if (!d_er) memcpy(er, t_er, N * 4);
+    if (!d_el) memcpy(el, t_el, N * 4);
+    if (!d_done) memcpy(done, t_done, N);
+    if (!d_to) memcpy(to, t_to, N);
     E->host_t[0] = t1 - t0; E->host_t[1] = t2 - t1; E->host_t[2] = t3 - t2; E->host_t[3] = now() - t3;
-    if (any & (1 << 16)) return fail(SS_ERR_ARG, "ss_step_host: non-finite action");      // (the kernel's own check; unreachable after the host's)
     return SS_OK;
 }
 
@@ -1267,10 +1266,10 @@ int ss_reset_host(ss_env* E, float* obs) {
     if (!E || !obs) return fail(SS_ERR_ARG, "ss_reset_host: null buffer");
     CK(cudaSetDevice(E->device));
     int rc = ensure_staging(E); if (rc) return rc;
-    bool direct; float* ot = obs_target(E, obs, &direct);
+    bool direct; float* ot = (float*)out_target(obs, E->h_out + (size_t)E->n * 8, &direct);
     rc = ss_reset_all(E, ot, E->own); if (rc) return rc;
     CK(cudaStreamSynchronize(E->own));
-    if (!direct) memcpy(obs, E->h_obs, (size_t)E->n * SS_OBS * 4);
+    if (!direct) memcpy(obs, ot, (size_t)E->n * SS_OBS * 4);
     return SS_OK;
 }
 

@@ -224,13 +224,14 @@ class BatchedStepperEnv:
                                       "statistics on the device (steppingstone_b200.collector.EpisodeStats)")
         self._monitor = _MonitorLog(log_dir, self.first_env, N, env_id, self._t0) if log_dir else None
         if output == "numpy":
-            self._timeout = np.zeros(N, np.uint8)
-            self._ep_ret = np.zeros(N, np.float32)
-            self._ep_len = np.zeros(N, np.int32)
+            # every output array is pinned host memory: ss_step_host lets the kernel write into it directly
+            self._timeout = _pinned_array(self._lib, (N,), np.uint8); self._timeout[:] = 0
+            self._ep_ret = _pinned_array(self._lib, (N,), np.float32); self._ep_ret[:] = 0
+            self._ep_len = _pinned_array(self._lib, (N,), np.int32); self._ep_len[:] = 0
             self._stat_ptrs = (self._timeout.ctypes.data, self._ep_ret.ctypes.data, self._ep_len.ctypes.data)
             self._pool_obs = _ArrayPool((N, OBS_DIM), np.float32, factory=lambda: _pinned_array(self._lib, (N, OBS_DIM), np.float32))
-            self._pool_rew = _ArrayPool((N,), np.float64)
-            self._pool_done = _ArrayPool((N,), np.bool_)
+            self._pool_rew = _ArrayPool((N,), np.float64, factory=lambda: _pinned_array(self._lib, (N,), np.float64))
+            self._pool_done = _ArrayPool((N,), np.bool_, factory=lambda: _pinned_array(self._lib, (N,), np.bool_))
         else:
             import torch
             self._torch = torch

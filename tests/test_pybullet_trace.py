@@ -1,7 +1,8 @@
 """Tier-2 parity: the oracle against traces recorded from the real PyBullet reference.
 
-tools/record_pybullet_trace.py writes tests/golden/pybullet_*.npz wherever pybullet + gym are installed; the build image
-has neither, so these tests SKIP there and the rigid-body arithmetic stays "parity unpinned" (DESIGN.md section 5).
+tools/record_pybullet_trace.py writes tests/golden/pybullet_*.npz wherever pybullet + gym are installed; neither the build
+image nor the GPU box has them (probed in round 2: profiles/r02a_probe_reference_deps.log -- no module, no wheel, no network),
+so these tests SKIP and the rigid-body arithmetic stays "parity unpinned" (DESIGN.md section 5).
 With fixtures present: (1) the compiled model tables against getDynamicsInfo / getJointInfo; (2) one control step of
 the oracle from every recorded state against the next recorded state (teacher forcing, so no trajectory divergence),
 at the north star's stated tolerance: 1e-3 relative on velocities in contact, 1e-5 on positions."""
@@ -14,7 +15,7 @@ import pytest
 from conftest import ROOT, make_oracle
 
 TRACES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "pybullet_*.npz")))
-pytestmark = pytest.mark.skipif(not TRACES, reason="no PyBullet traces (tools/record_pybullet_trace.py needs pybullet; parity unpinned)")
+pytestmark = pytest.mark.skipif(not TRACES, reason="no PyBullet traces (tools/record_pybullet_trace.py needs pybullet: absent from every box, profiles/r02a_probe_reference_deps.log; parity unpinned)")
 
 
 @pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[:-4] for p in TRACES])

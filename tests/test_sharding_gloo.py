@@ -46,6 +46,10 @@ def _worker(rank, world, port, q):
             setattr(ro, f, full[f][:, first:first + k].clone())
         gathered = sharding.gather_rollout(ro)
         ok = all(torch.equal(gathered[f], full[f]) for f in sharding.ROLLOUT_FIELDS)
+        # rank-major (no env-axis transpose): [world, T+1, N_local, .] -- rank r's shard sits in block r
+        rm = sharding.gather_rollout(ro, rank_major=True)
+        ok = ok and all(tuple(rm[f].shape) == (world, T + 1, k, 3) for f in sharding.ROLLOUT_FIELDS)
+        ok = ok and all(torch.equal(rm[f][r], full[f][:, r * k:(r + 1) * k]) for f in sharding.ROLLOUT_FIELDS for r in range(world))
         adv = full["returns"][:-1] - full["value_preds"][:-1]
         mean, std = sharding.global_advantage_stats(adv[:, first:first + k])
         ok = ok and abs(float(mean) - float(adv.mean())) < 1e-6 and abs(float(std) - float(adv.std())) < 1e-6

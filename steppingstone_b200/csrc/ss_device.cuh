@@ -29,6 +29,10 @@
 namespace ssb {
 
 constexpr int NB = SS_NB, NJ = SS_NJ, ND = SS_NDOF;
+#ifndef SS_DEL_UNROLL
+#define SS_DEL_UNROLL 7      // the Delassus accumulation loop fully unrolled over its 7 dof chunks: every shared-memory address an
+#endif                       // immediate, the live-group tests hoisted -- 0.7066 -> 0.6569 ms per 8192-env step (1 = the rolled loop)
+constexpr int DEL_UNROLL = SS_DEL_UNROLL;
 constexpr int HS = 28;   // row stride of H / L in shared memory: 16-byte aligned rows; a lane reads ITS row with 7 LDS.128
                          // (quarter-warp addresses 112 B apart hit disjoint bank groups -> conflict-free)
 constexpr int ZS = 28;   // row stride of Z (same access pattern)
@@ -1138,7 +1142,7 @@ __device__ __forceinline__ int substep_warp(const DevModel& M, WarpSmem& W, floa
         {
             const float4* Z4 = reinterpret_cast<const float4*>(Z);
             const float4* D4 = reinterpret_cast<const float4*>(W.dinv);
-#pragma unroll 1
+#pragma unroll DEL_UNROLL
             for (int j = 0; j < ZS / 4; j++) {
                 const float4 o = Z4[r * (ZS / 4) + j], d = D4[j];
                 const float w0 = o.x * d.x, w1 = o.y * d.y, w2 = o.z * d.z, w3 = o.w * d.w;

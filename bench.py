@@ -488,7 +488,7 @@ def run_b200(args, wl):
     acts_h = acts[:ring_h].cpu().numpy()
     Ke = max(8, min(K, 64))
     for i in range(3):
-        env_h.step(acts_h[i % ring_h])
+        obs_h, rew_h, done_h, infos_h = env_h.step(acts_h[i % ring_h])     # held like in the timed loop (output array rotation)
     barrier()
     host4 = np.zeros(4); out4 = np.zeros(4)
     t0 = time.perf_counter()

@@ -149,6 +149,13 @@ class _ArrayPool:
             self.items.append((a, ptr))
         return a, ptr
 
+    def prefill(self, n=2):
+        """Allocate the arrays a caller that keeps the previous step's outputs alternates between (pinning memory costs
+        milliseconds: not inside somebody's first steps)."""
+        while len(self.items) < min(n, self.depth):
+            a = self.factory()
+            self.items.append((a, a.ctypes.data))
+
 
 class _PinnedBlock:
     """cudaHostAlloc'ed memory owned by a Python object (freed when the last array over it dies)."""
@@ -232,6 +239,8 @@ class BatchedStepperEnv:
             self._pool_obs = _ArrayPool((N, OBS_DIM), np.float32, factory=lambda: _pinned_array(self._lib, (N, OBS_DIM), np.float32))
             self._pool_rew = _ArrayPool((N,), np.float64, factory=lambda: _pinned_array(self._lib, (N,), np.float64))
             self._pool_done = _ArrayPool((N,), np.bool_, factory=lambda: _pinned_array(self._lib, (N,), np.bool_))
+            for pool in (self._pool_obs, self._pool_rew, self._pool_done):
+                pool.prefill()
         else:
             import torch
             self._torch = torch

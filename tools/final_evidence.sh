@@ -9,6 +9,8 @@ ncu -i gpurun_out/${TAG}_step.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.c
 ncu -i gpurun_out/${TAG}_step.ncu-rep --page source --csv > gpurun_out/${TAG}_sass.csv 2>/dev/null
 python tools/ncu_summary.py gpurun_out/${TAG}_raw.csv ${TAG} > /dev/null && cp profiles/traffic.json gpurun_out/${TAG}_traffic.json && cp profiles/${TAG}_env_step_ncu.csv gpurun_out/
 python tools/ncu_opcodes.py gpurun_out/${TAG}_sass.csv > gpurun_out/${TAG}_env_step_opcodes.txt 2>/dev/null
+# per-phase table (needs the disassembly of the .so that ran):  cuobjdump -xelf all libss_b200.so; nvdisasm -g -c *.cubin > all.sass;
+#   python tools/ncu_phases.py gpurun_out/${TAG}_sass.csv all.sass env_step_kernelILb0 > profiles/${TAG}_env_step_phases.txt
 python bench.py --steps 256 --warmup 32 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 200 gpurun_out/${TAG}_bench.err
 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference_arm.json 2>/dev/null
 python bench.py --workload mike --steps 128 --warmup 16 --no-cpu-baseline > gpurun_out/${TAG}_bench_mike.json 2>/dev/null
